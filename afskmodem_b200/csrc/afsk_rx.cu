@@ -1,0 +1,809 @@
+// afsk_rx.cu — receiver path of libafsk_b200.so (sm_100a).
+//
+// Replaces the compute of Receiver.load (afskmodem.py:420-430) for a batch of independent
+// captures with three kernels:
+//
+//   k_clock   __recoverClockIndex (:322-339): first 4096 frames -> prefix sum in shared memory,
+//             every candidate offset scored from 7 prefix look-ups (closed form of getDiff
+//             against the +/-full-scale training cycle), block arg-min with first-index ties.
+//   k_demod   __decodeBit (:342-351) + __amplify (:287-296) + getAmplitude (:94-98) for EVERY
+//             bit window of every capture: the streaming, HBM-bound kernel.  Persistent CTAs,
+//             1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a multi-stage shared-memory ring
+//             fed by a producer warp, mbarrier full/empty hand-off, consumers read 128-bit
+//             vectors and reduce each window to a mark/space decision bit and a "quiet" bit with
+//             packed 16x2 integer ops and IDP.2A dot products.  Output: 2 bits per window.
+//   k_frame   __scanTraining (:386-390) terminator search, the data loop's end detector (:372-378),
+//             ECC.decode (:154-163) and __bitsToBytes (:393-399) on the packed bit planes.
+//
+// All arithmetic is integer and bit-exact with the reference (see DESIGN.md for the algebra).
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "afsk_common.cuh"
+
+namespace {
+
+constexpr int kConsumerThreads = 256;
+constexpr int kDemodThreads = kConsumerThreads + 32;   // + one producer warp
+constexpr int kMaxStages = 8;
+constexpr int kClockThreads = 128;
+constexpr int kFrameThreads = 128;
+
+struct __align__(16) CapDesc {
+    int64_t off;         // first sample of the capture (global sample index)
+    int64_t n;           // samples in the capture
+    int64_t plane_base;  // word offset of the capture's rows in the bit / quiet planes
+    int64_t out_off;     // byte offset of the capture's decoded payload
+    int32_t bf;          // Receiver.__bit_frames (:277)
+    int32_t thr;         // amp_end_threshold clamped to [0, 65537]
+    int32_t status0;     // 0 -> decode on the GPU; otherwise the final AFSK_ST_* status
+    int32_t group;       // index of the baud group (kernel launch) the capture belongs to
+};
+
+struct __align__(16) TileMeta {
+    int32_t e0;          // first window's sample offset inside the 16-byte aligned copy
+    int32_t nwin;        // valid windows in this tile (0 -> nothing to do)
+    int32_t thr_bf;      // amp_end * bf : quiet <=> sum|x| < thr_bf
+    int32_t pad;
+    int64_t word_base;   // plane word receiving window 0 of the tile
+    int64_t pad2;
+};
+
+struct DemodParams {
+    const int16_t *samples;
+    const CapDesc *caps;
+    const int32_t *clock;
+    const int32_t *gcaps;        // capture ids of this group, ascending
+    const int32_t *gtile_first;  // [ng + 1] prefix of tile counts over gcaps
+    uint32_t *bits;
+    uint32_t *quiet;
+    int ng;
+    int total_items;
+    int bf;
+    int tpw_log2;     // threads per window = 1 << tpw_log2
+    int seg;          // samples per thread segment = ceil(bf / tpw)
+    int nv;           // 16-byte vectors each thread reads
+    int wt;           // windows per tile = kConsumerThreads >> tpw_log2
+    int stage_bytes;
+    int stages;
+};
+
+__device__ __forceinline__ long long num_windows(long long n, int bf, int clk)
+{
+    // K = #{k >= 0 : clk + k*bf < n - bf}   (afskmodem.py:362,372 — strict)
+    long long span = n - bf - clk;
+    return span > 0 ? (span + bf - 1) / bf : 0;
+}
+
+// ------------------------------------------------------------------------------ k_clock ----
+__global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restrict__ x,
+                                                         const CapDesc *__restrict__ caps,
+                                                         int32_t *__restrict__ clock,
+                                                         AfskRxResult *__restrict__ res)
+{
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CapDesc d = caps[c];
+    if (d.status0 != 0) {
+        if (tid == 0) {
+            clock[c] = -1;
+            AfskRxResult r;
+            r.status = d.status0; r.clock = -1; r.train_end = -1; r.nbits = 0; r.nbytes = 0;
+            res[c] = r;
+        }
+        return;
+    }
+    // y = 4104 samples starting at the 16-byte boundary at or below the capture start
+    __shared__ uint32_t P[AFSK_SYNC_FRAMES + 8 + 1];   // P[i] = sum y[0..i)  (mod 2^32)
+    __shared__ uint32_t warp_tot[kClockThreads / 32];
+    __shared__ uint32_t warp_min[kClockThreads / 32];
+    const int64_t ga = d.off & ~(int64_t)7;
+    const int e = (int)(d.off - ga);
+    const uint4 *src = reinterpret_cast<const uint4 *>(x + ga);
+    // 128*4 = 512 vectors cover the scan when the capture is 16-byte aligned; one more otherwise
+    const int nvec = (tid == kClockThreads - 1 && e > 0) ? 5 : 4;
+    int32_t loc[40];
+    uint32_t run = 0;
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+        if (v < nvec) {
+            uint4 q = ld_nc_v4(src + tid * 4 + v);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int lo = (int)(int16_t)(w[j] & 0xFFFF), hi = (int)(int16_t)(w[j] >> 16);
+                run += (uint32_t)lo; loc[v * 8 + 2 * j] = (int32_t)run;
+                run += (uint32_t)hi; loc[v * 8 + 2 * j + 1] = (int32_t)run;
+            }
+        }
+    }
+    // exclusive scan of the per-thread totals
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t base = inc - run;
+    for (int w = 0; w < warp; w++) base += warp_tot[w];
+    if (tid == 0) P[0] = 0;
+#pragma unroll
+    for (int v = 0; v < 5; v++)
+        if (v < nvec)
+#pragma unroll
+            for (int k = 0; k < 8; k++) P[(tid * 4 + v) * 8 + k + 1] = base + (uint32_t)loc[v * 8 + k];
+    __syncthreads();
+
+    const int bf = d.bf, q = bf >> 2, h = bf >> 1;
+    const int span = AFSK_SYNC_FRAMES - 2 * bf;                 // :327
+    const uint32_t c0 = 65535u * (uint32_t)bf;
+    const uint32_t div = 2u * (uint32_t)bf;
+    uint32_t best = 0xFFFFFFFFu;
+    for (int i = tid; i < span; i += kClockThreads) {
+        const int b = i + e;
+        // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO)
+        uint32_t D = c0 + P[b] - 2u * P[b + q] + 2u * P[b + 2 * q] - 2u * P[b + 3 * q] + 2u * P[b + bf] -
+                     2u * P[b + bf + h] + P[b + 2 * bf];
+        uint32_t dq = D / div;                                  // getDiff :107
+        uint32_t key = (dq << 12) | (uint32_t)i;                // first strict minimum :332-337
+        best = min(best, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+    if (lane == 0) warp_min[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kClockThreads / 32; w++) best = min(best, warp_min[w]);
+        clock[c] = (int32_t)(best & 0xFFFu);
+    }
+}
+
+// ------------------------------------------------------------------------------ k_demod ----
+// One 32-bit word = two int16 samples.  Returns through the three accumulators:
+//   accM/accS += sum_j T[j] * v_j   with v = +4097 (x > 512), -1 (x < -512), 0 otherwise
+//   accA      += sum_j in-window |x_j|
+// wt packs the +/-1/0 template weights: bytes {mark_lo, mark_hi, space_lo, space_hi}.
+template <bool kAmpHi>
+__device__ __forceinline__ void accum_word(uint32_t w, uint32_t wt, uint32_t aw, int &accM, int &accS,
+                                           unsigned &accA)
+{
+    const uint32_t m = prmt(w, 0u, 0xBB99u);          // per-half sign mask (0xFFFF where x < 0)
+    const uint32_t a = w ^ m;                         // ones'-complement magnitude
+    const uint32_t ap = a + (m & 0x00010001u);        // |x| as u16 (32768 for -32768), no carry across halves
+    const uint32_t t = ap + 0x7DFF7DFFu;              // bit 15 of each half <=> |x| >= 513  (__amplify :290-292)
+    const uint32_t nzm = prmt(t, 0u, 0xBB99u);        // 0xFFFF where |x| > 512
+    const uint32_t v = nzm & (m | 0x10011001u);       // +4097 / -1 / 0
+    accM = __dp2a_lo((int)v, (int)wt, accM);
+    accS = __dp2a_hi((int)v, (int)wt, accS);
+    accA = kAmpHi ? __dp2a_hi(ap, aw, accA) : __dp2a_lo(ap, aw, accA);
+}
+
+// mark_diff < space_diff (afskmodem.py:346-351) from the packed correlations.
+__device__ __forceinline__ bool decide_bit(int accM, int accS, int bf)
+{
+    // acc = 4096*X + U,  X = T.p, U = T.(p-n), |U| <= bf <= 2047
+    const int Um = (int)((unsigned)accM << 20) >> 20, Xm = (accM - Um) >> 12, Wm = 2 * Xm - Um;   // W = T.(p+n)
+    const int Us = (int)((unsigned)accS << 20) >> 20, Xs = (accS - Us) >> 12, Ws = 2 * Xs - Us;
+    // sum_j |T[j] - amp[j]| = (65535*(bf - U) + W) / 2   (always even)
+    const int M = (65535 * (bf - Um) + Wm) >> 1;
+    const int S = (65535 * (bf - Us) + Ws) >> 1;
+    if (S <= M) return false;
+    if (S - M >= bf) return true;
+    return M < (S / bf) * bf;                          // floor(M/bf) < floor(S/bf)
+}
+
+__global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.stages;
+    const int tpw = 1 << p.tpw_log2;
+    uint8_t *stage_base = smem;
+    uint4 *wtab = reinterpret_cast<uint4 *>(smem + (size_t)S * p.stage_bytes);
+    const int wtab_entries = tpw * 8 * p.nv;                       // 32 bytes each
+    TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + 2 * wtab_entries);
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
+    uint64_t *empty = full + kMaxStages;
+    uint8_t *resbuf = reinterpret_cast<uint8_t *>(empty + kMaxStages);   // [2][kConsumerThreads]
+
+    // ---- template weight table: entry (part, e, i) covers samples r = 8i + 2j + h - e of the
+    //      thread segment; window position p = part*seg + r; quarter p/q selects the template sign.
+    {
+        const int q = p.bf >> 2;
+        for (int idx = tid; idx < wtab_entries; idx += kDemodThreads) {
+            const int i = idx % p.nv, e = (idx / p.nv) & 7, part = idx / (p.nv * 8);
+            const int seg_lo = part * p.seg, seg_hi = min(p.bf, seg_lo + p.seg);
+            uint32_t ms[4], amp[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                ms[j] = 0;
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int r = 8 * i + 2 * j + hh - e, pos = seg_lo + r;
+                    if (r >= 0 && pos < seg_hi) {
+                        const int qd = pos / q;
+                        const uint32_t mk = (qd & 1) ? 0xFFu : 0x01u;   // mark : + - + -
+                        const uint32_t sp = (qd & 2) ? 0xFFu : 0x01u;   // space: + + - -
+                        ms[j] |= (mk << (8 * hh)) | (sp << (16 + 8 * hh));
+                        amp[j >> 1] |= 1u << (8 * (2 * (j & 1) + hh));
+                    }
+                }
+            }
+            wtab[2 * idx] = make_uint4(ms[0], ms[1], ms[2], ms[3]);
+            wtab[2 * idx + 1] = make_uint4(amp[0], amp[1], 0u, 0u);
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int per = (p.total_items + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per;
+    const int hi = min(p.total_items, lo + per);
+    if (lo >= hi) return;
+
+    if (warp == kConsumerThreads / 32) {
+        // ------------------------------------------------------------ producer warp ----
+        if (lane != 0) return;
+        int a = 0, b = p.ng;
+        while (b - a > 1) {
+            const int mid = (a + b) >> 1;
+            if (p.gtile_first[mid] <= lo) a = mid; else b = mid;
+        }
+        int ci = a, this_first = p.gtile_first[ci], next_first = p.gtile_first[ci + 1];
+        bool have = false;
+        CapDesc d;
+        long long K = 0;
+        int clk = 0;
+        for (int it = lo; it < hi; ++it) {
+            while (it >= next_first) {
+                ci++;
+                this_first = next_first;
+                next_first = p.gtile_first[ci + 1];
+                have = false;
+            }
+            if (!have) {
+                const int c = p.gcaps[ci];
+                d = p.caps[c];
+                clk = p.clock[c];
+                K = num_windows(d.n, p.bf, clk);
+                have = true;
+            }
+            const long long k0t = (long long)(it - this_first) * p.wt;
+            long long nw = K - k0t;
+            const int nwin = nw <= 0 ? 0 : (nw > p.wt ? p.wt : (int)nw);
+            const long long g0 = d.off + clk + k0t * p.bf;          // first sample of the tile
+            const long long ga = g0 & ~7LL;
+            const int n = it - lo, s = n % S;
+            if (n >= S) mbar_wait(&empty[s], ((n / S) & 1) ^ 1);
+            TileMeta m;
+            m.e0 = (int)(g0 - ga);
+            m.nwin = nwin;
+            m.thr_bf = d.thr * p.bf;
+            m.pad = 0;
+            m.word_base = d.plane_base + (k0t >> 5);
+            m.pad2 = 0;
+            meta[s] = m;
+            if (nwin > 0) {
+                const uint32_t bytes = (uint32_t)((((long long)m.e0 + (long long)nwin * p.bf) * 2 + 15) & ~15LL);
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(stage_base + (size_t)s * p.stage_bytes, p.samples + ga, bytes, &full[s]);
+            } else {
+                mbar_arrive(&full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers ----
+    const int w = tid >> p.tpw_log2, part = tid & (tpw - 1);
+    const int bf = p.bf, nv = p.nv;
+    const int rel0 = w * bf + part * p.seg;
+    for (int n = 0; n < hi - lo; ++n) {
+        const int s = n % S;
+        mbar_wait(&full[s], (n / S) & 1);
+        const TileMeta m = meta[s];
+        bool bit = false, quiet = false;
+        if (m.nwin > 0) {
+            const int rel = m.e0 + rel0;
+            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (rel >> 3);
+            const uint4 *wp = wtab + 2 * ((part * 8 + (rel & 7)) * nv);
+            int accM = 0, accS = 0;
+            unsigned accA = 0;
+#pragma unroll 2
+            for (int i = 0; i < nv; i++) {
+                const uint4 dv = dp[i];
+                const uint4 wv = wp[2 * i];
+                const uint2 av = *reinterpret_cast<const uint2 *>(wp + 2 * i + 1);
+                accum_word<false>(dv.x, wv.x, av.x, accM, accS, accA);
+                accum_word<true>(dv.y, wv.y, av.x, accM, accS, accA);
+                accum_word<false>(dv.z, wv.z, av.y, accM, accS, accA);
+                accum_word<true>(dv.w, wv.w, av.y, accM, accS, accA);
+            }
+            for (int o = 1; o < tpw; o <<= 1) {
+                accM += __shfl_xor_sync(0xFFFFFFFFu, accM, o);
+                accS += __shfl_xor_sync(0xFFFFFFFFu, accS, o);
+                accA += __shfl_xor_sync(0xFFFFFFFFu, accA, o);
+            }
+            const bool valid = (part == 0) && (w < m.nwin);
+            bit = valid && decide_bit(accM, accS, bf);
+            quiet = valid && ((int)accA < m.thr_bf);            // getAmplitude(chunk) < amp_end :375
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);                   // stage may be refilled
+        if (m.nwin > 0) {
+            if (p.tpw_log2 == 0) {
+                const uint32_t bw = __ballot_sync(0xFFFFFFFFu, bit);
+                const uint32_t qw = __ballot_sync(0xFFFFFFFFu, quiet);
+                if (lane == 0 && warp * 32 < m.nwin) {
+                    p.bits[m.word_base + warp] = bw;
+                    p.quiet[m.word_base + warp] = qw;
+                }
+            } else {
+                uint8_t *rb = resbuf + (n & 1) * kConsumerThreads;
+                if (part == 0) rb[w] = (uint8_t)((bit ? 1 : 0) | (quiet ? 2 : 0));
+                asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+                if (warp * 32 < p.wt) {
+                    const uint8_t r = rb[warp * 32 + lane];
+                    const uint32_t bw = __ballot_sync(0xFFFFFFFFu, r & 1);
+                    const uint32_t qw = __ballot_sync(0xFFFFFFFFu, r & 2);
+                    if (lane == 0 && warp * 32 < m.nwin) {
+                        p.bits[m.word_base + warp] = bw;
+                        p.quiet[m.word_base + warp] = qw;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ k_frame ----
+__device__ __forceinline__ long long block_min_ll(long long v, long long *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    __syncthreads();                       // scratch reuse
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    long long r = scratch[0];
+    for (int w = 1; w < kFrameThreads / 32; w++) r = min(r, scratch[w]);
+    return r;
+}
+
+__device__ __forceinline__ uint32_t hamming74_nibble(uint32_t cw)
+{
+    // ECC.__decodeNibble :145-151 — cw bit i = c_i (c0 first received)
+    const uint32_t s0 = __popc(cw & 0x55u) & 1u;   // c0^c2^c4^c6
+    const uint32_t s1 = __popc(cw & 0x66u) & 1u;   // c1^c2^c5^c6
+    const uint32_t s2 = __popc(cw & 0x78u) & 1u;   // c3^c4^c5^c6
+    const uint32_t e = 4u * s2 + 2u * s1 + s0;
+    if (e) cw ^= 1u << (e - 1u);
+    return (((cw >> 2) & 1u) << 3) | (((cw >> 4) & 1u) << 2) | (((cw >> 5) & 1u) << 1) | ((cw >> 6) & 1u);
+}
+
+__global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restrict__ caps,
+                                                         const int32_t *__restrict__ clock,
+                                                         const uint32_t *__restrict__ bits,
+                                                         const uint32_t *__restrict__ quiet,
+                                                         uint8_t *__restrict__ out,
+                                                         AfskRxResult *__restrict__ res)
+{
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const CapDesc d = caps[c];
+    if (d.status0 != 0) return;
+    __shared__ long long scratch[kFrameThreads / 32];
+    const int clk = clock[c];
+    const long long K = num_windows(d.n, d.bf, clk);
+    const long long nwords = (K + 31) >> 5;
+    const uint32_t *B = bits + d.plane_base;
+    const uint32_t *Q = quiet + d.plane_base;
+    const long long NONE = 0x7FFFFFFFFFFFFFFFLL;
+
+    // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
+    long long kterm = NONE;
+    for (long long base = 0; base < nwords; base += kFrameThreads) {
+        const long long j = base + tid;
+        long long cand = NONE;
+        if (j < nwords) {
+            const uint64_t v = ((uint64_t)B[j] << 32) | (j ? B[j - 1] : 0u);
+            uint32_t M = (uint32_t)((v >> 29) & ~(v >> 30) & ~(v >> 31) & ~(v >> 32));
+            const long long rem = K - 32 * j;
+            if (rem < 32) M &= (1u << rem) - 1u;
+            if (M) cand = 32 * j + (__ffs(M) - 1);
+        }
+        kterm = block_min_ll(cand, scratch);
+        if (kterm != NONE) break;
+    }
+    const long long k0 = (kterm == NONE) ? K : kterm + 1;
+    // phase 2 (:372-378): first quiet window at or after k0
+    long long k1 = NONE;
+    for (long long base = k0 >> 5; base < nwords; base += kFrameThreads) {
+        const long long j = base + tid;
+        long long cand = NONE;
+        if (j < nwords) {
+            uint32_t M = Q[j];
+            if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
+            const long long rem = K - 32 * j;
+            if (rem < 32) M &= (1u << rem) - 1u;
+            if (M) cand = 32 * j + (__ffs(M) - 1);
+        }
+        k1 = block_min_ll(cand, scratch);
+        if (k1 != NONE) break;
+    }
+    if (k1 == NONE) k1 = K;
+    const long long nbits = k1 - k0;
+    const long long nbytes = (nbits / 7) / 2;        // ECC.decode :156, __bitsToBytes :396
+    uint8_t *o = out + d.out_off;
+    for (long long i = tid; i < nbytes; i += kFrameThreads) {
+        const long long pos = k0 + 14 * i;
+        const uint32_t lo = B[pos >> 5], hi = B[(pos >> 5) + 1];
+        const uint32_t val = __funnelshift_r(lo, hi, (uint32_t)(pos & 31));
+        o[i] = (uint8_t)((hamming74_nibble(val & 0x7Fu) << 4) | hamming74_nibble((val >> 7) & 0x7Fu));
+    }
+    if (tid == 0) {
+        AfskRxResult r;
+        r.status = nbits > 0 ? AFSK_ST_OK : AFSK_ST_NO_DATA;
+        r.clock = clk;
+        r.train_end = (long long)clk + k0 * d.bf;     // "Training sequence terminated on frame" :368
+        r.nbits = nbits;
+        r.nbytes = nbits > 0 ? nbytes : 0;
+        res[c] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------- k_gate ----
+// Receiver.__listen (:299-319) arithmetic: per-2048-frame chunk amplitude, then open/close search.
+__global__ void __launch_bounds__(256) k_gate_amp(const int16_t *__restrict__ x, const int64_t *__restrict__ chunk_first,
+                                                  const int64_t *__restrict__ off, int S, long long total_chunks,
+                                                  int32_t *__restrict__ amp)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= total_chunks) return;
+    int a = 0, b = S;                       // stream of this chunk
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (chunk_first[mid] <= gw) a = mid; else b = mid;
+    }
+    const int16_t *src = x + off[a] + (gw - chunk_first[a]) * AFSK_GATE_CHUNK;
+    uint32_t sum = 0;
+    for (int i = lane; i < AFSK_GATE_CHUNK; i += 32) {
+        const int v = src[i];
+        sum += (uint32_t)(v < 0 ? -v : v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) amp[gw] = (int32_t)(sum / AFSK_GATE_CHUNK);          // getAmplitude :94-98
+}
+
+__global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__restrict__ amp,
+                                                             const int64_t *__restrict__ chunk_first, int amp_start,
+                                                             int amp_end, long long timeout_frames,
+                                                             int64_t *__restrict__ range)
+{
+    const int s = blockIdx.x, tid = threadIdx.x;
+    __shared__ long long scratch[kFrameThreads / 32];
+    const long long NONE = 0x7FFFFFFFFFFFFFFFLL;
+    const int32_t *A = amp + chunk_first[s];
+    const long long nch = chunk_first[s + 1] - chunk_first[s];
+    // chunk idx >= 1 is examined iff (idx-1)*2048 < timeout_frames  (:304,:310)
+    long long lim = timeout_frames <= 0 ? 0 : (timeout_frames + AFSK_GATE_CHUNK - 1) / AFSK_GATE_CHUNK;  // idx <= lim
+    long long last = min(nch - 1, lim);
+    long long open = NONE;
+    for (long long base = 1; base <= last; base += kFrameThreads) {
+        const long long j = base + tid;
+        long long cand = (j <= last && A[j] > amp_start) ? j : NONE;     // :306
+        open = block_min_ll(cand, scratch);
+        if (open != NONE) break;
+    }
+    long long close = NONE;
+    if (open != NONE) {
+        for (long long base = open + 1; base < nch; base += kFrameThreads) {
+            const long long j = base + tid;
+            long long cand = (j < nch && A[j] < amp_end) ? j : NONE;     // :316
+            close = block_min_ll(cand, scratch);
+            if (close != NONE) break;
+        }
+    }
+    if (tid == 0) {
+        if (open == NONE) {
+            range[3 * s] = 0; range[3 * s + 1] = 0; range[3 * s + 2] = 0;
+        } else {
+            range[3 * s] = 1;
+            range[3 * s + 1] = open * AFSK_GATE_CHUNK;
+            range[3 * s + 2] = (close == NONE ? (nch > open + 1 ? nch : open + 1) : close + 1) * AFSK_GATE_CHUNK;
+        }
+    }
+}
+
+struct Group {
+    int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, wt = 0, stage_bytes = 0, stages = 0;
+    size_t smem = 0;
+    int grid = 0;
+    std::vector<int32_t> caps, tile_first;
+    int32_t *d_caps = nullptr, *d_tile_first = nullptr;
+};
+
+}  // namespace
+
+struct AfskRxPlan {
+    int device = 0;
+    int B = 0;
+    int sm_count = 148;
+    std::vector<CapDesc> caps;
+    std::vector<int64_t> out_off;
+    std::vector<Group> groups;
+    CapDesc *d_caps = nullptr;
+    int32_t *d_clock = nullptr;
+    uint32_t *d_bits = nullptr, *d_quiet = nullptr;
+    int64_t plane_words = 0;
+};
+
+static size_t demod_smem_bytes(const Group &g)
+{
+    return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * 8 * g.nv * 32 +
+           kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t) + 2 * kConsumerThreads;
+}
+
+static bool configure_group(Group &g, int bf)
+{
+    g.bf = bf;
+    g.tpw_log2 = 0;
+    while ((bf >> g.tpw_log2) > 48 && g.tpw_log2 < 3) g.tpw_log2++;
+    const int tpw = 1 << g.tpw_log2;
+    g.seg = (bf + tpw - 1) / tpw;
+    g.nv = (g.seg + 6) / 8 + 1;
+    g.wt = kConsumerThreads / tpw;
+    g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 128) + 127) & ~127;   // copy + over-read slack
+    const size_t budget = 100 * 1024;   // two CTAs per SM
+    g.stages = (int)std::min<size_t>(4, std::max<size_t>(1, budget / g.stage_bytes));
+    g.smem = demod_smem_bytes(g);
+    while (g.smem > 227 * 1024 && g.stages > 1) {
+        g.stages--;
+        g.smem = demod_smem_bytes(g);
+    }
+    return g.smem <= 227 * 1024;
+}
+
+extern "C" {
+
+int64_t afsk_rx_out_capacity(int64_t n_samples, int baud)
+{
+    int bf, ml, sl;
+    if (n_samples <= 0 || !afsk_tone_geometry(baud, &bf, &ml, &sl)) return 16;
+    return (n_samples / bf) / 14 + 16;
+}
+
+int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32_t *h_baud,
+                        const int32_t *h_amp_end, AfskRxPlan **plan_out)
+{
+    if (!plan_out || B < 0 || (B > 0 && (!h_offsets || !h_baud || !h_amp_end))) {
+        afsk_set_error("afsk_rx_plan_create: bad argument");
+        return AFSK_E_ARG;
+    }
+    AfskDeviceGuard guard(device);
+    if (!guard.ok) { afsk_set_error("cannot select device %d", device); return AFSK_E_CUDA; }
+    AfskRxPlan *P = new (std::nothrow) AfskRxPlan();
+    if (!P) return AFSK_E_ARG;
+    P->device = device;
+    P->B = B;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) P->sm_count = sms;
+    P->caps.resize(B);
+    P->out_off.assign(B + 1, 0);
+    std::map<int, int> bf_to_group;
+    int64_t words = 0;
+    for (int c = 0; c < B; c++) {
+        CapDesc &d = P->caps[c];
+        d.off = h_offsets[c];
+        d.n = h_offsets[c + 1] - h_offsets[c];
+        if (d.n < 0 || d.off < 0) { delete P; afsk_set_error("offsets must be non-decreasing"); return AFSK_E_ARG; }
+        d.plane_base = words;
+        d.out_off = P->out_off[c];
+        d.group = -1;
+        int bf = 0, ml = 0, sl = 0;
+        long long thr = h_amp_end[c];
+        d.thr = (int32_t)std::min<long long>(std::max<long long>(thr, 0), 65537);
+        if (!afsk_tone_geometry(h_baud[c], &bf, &ml, &sl)) {
+            d.bf = 0; d.status0 = AFSK_ST_EXC_BAUD;
+        } else {
+            d.bf = bf;
+            if (d.n < AFSK_SYNC_FRAMES) d.status0 = AFSK_ST_NO_CLOCK;                 // :323-325
+            else if (AFSK_SYNC_FRAMES - 2 * bf <= 0) d.status0 = AFSK_ST_EXC_INDEX;   // :332 on []
+            else if (ml != bf || sl != bf) d.status0 = AFSK_ST_EXC_WAVELEN;           // :102-103
+            else d.status0 = 0;
+        }
+        int64_t cap_bytes = 16;
+        if (d.status0 == 0) {
+            auto it = bf_to_group.find(bf);
+            if (it == bf_to_group.end()) {
+                Group g;
+                if (!configure_group(g, bf)) { delete P; afsk_set_error("bit_frames %d needs too much shared memory", bf); return AFSK_E_UNSUPPORTED; }
+                g.tile_first.push_back(0);
+                P->groups.push_back(g);
+                it = bf_to_group.emplace(bf, (int)P->groups.size() - 1).first;
+            }
+            Group &g = P->groups[it->second];
+            d.group = it->second;
+            const int64_t kmax = (d.n - bf + bf - 1) / bf;             // windows at clock 0
+            const int64_t ntiles = (kmax + g.wt - 1) / g.wt;
+            if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
+            g.caps.push_back(c);
+            g.tile_first.push_back(g.tile_first.back() + (int32_t)ntiles);
+            words += ntiles * (g.wt / 32) + 2;
+            cap_bytes = kmax / 14 + 16;
+        }
+        P->out_off[c + 1] = P->out_off[c] + cap_bytes;
+    }
+    P->plane_words = words + 8;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void **dptr, const void *src, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(dptr, bytes ? bytes : 16);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up((void **)&P->d_caps, P->caps.data(), sizeof(CapDesc) * B);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_clock, sizeof(int32_t) * (B ? B : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_bits, sizeof(uint32_t) * P->plane_words);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_quiet, sizeof(uint32_t) * P->plane_words);
+    for (Group &g : P->groups) {
+        up((void **)&g.d_caps, g.caps.data(), sizeof(int32_t) * g.caps.size());
+        up((void **)&g.d_tile_first, g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());
+        const int total = g.tile_first.back();
+        const int per_sm = g.smem <= 113 * 1024 ? 2 : 1;
+        g.grid = std::max(1, std::min(total, P->sm_count * per_sm));
+    }
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+        afsk_set_error("afsk_rx_plan_create: %s", cudaGetErrorString(e));
+        afsk_rx_plan_destroy(P);
+        return AFSK_E_CUDA;
+    }
+    *plan_out = P;
+    return AFSK_OK;
+}
+
+int afsk_rx_plan_destroy(AfskRxPlan *P)
+{
+    if (!P) return AFSK_OK;
+    AfskDeviceGuard guard(P->device);
+    cudaFree(P->d_caps); cudaFree(P->d_clock); cudaFree(P->d_bits); cudaFree(P->d_quiet);
+    for (Group &g : P->groups) { cudaFree(g.d_caps); cudaFree(g.d_tile_first); }
+    delete P;
+    return AFSK_OK;
+}
+
+int afsk_rx_plan_out_offsets(const AfskRxPlan *P, const int64_t **h_out_off)
+{
+    if (!P || !h_out_off) return AFSK_E_ARG;
+    *h_out_off = P->out_off.data();
+    return AFSK_OK;
+}
+
+int afsk_rx_plan_launches(const AfskRxPlan *P, int *launches)
+{
+    if (!P || !launches) return AFSK_E_ARG;
+    *launches = P->B > 0 ? 2 + (int)P->groups.size() : 0;
+    return AFSK_OK;
+}
+
+int afsk_rx_plan_planes(const AfskRxPlan *P, int capture, const uint32_t **d_bits, const uint32_t **d_quiet,
+                        int64_t *max_windows)
+{
+    if (!P || capture < 0 || capture >= P->B) return AFSK_E_ARG;
+    const CapDesc &d = P->caps[capture];
+    if (d_bits) *d_bits = P->d_bits + d.plane_base;
+    if (d_quiet) *d_quiet = P->d_quiet + d.plane_base;
+    if (max_windows) *max_windows = d.status0 == 0 ? (d.n - d.bf + d.bf - 1) / d.bf : 0;
+    return AFSK_OK;
+}
+
+int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, AfskRxResult *d_res, void *stream)
+{
+    if (!P || (P->B > 0 && (!d_samples || !d_out || !d_res))) { afsk_set_error("afsk_rx_decode: null argument"); return AFSK_E_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_samples) & 15) != 0) { afsk_set_error("afsk_rx_decode: d_samples must be 16-byte aligned"); return AFSK_E_ARG; }
+    if (P->B == 0) return AFSK_OK;
+    AfskDeviceGuard guard(P->device);
+    if (!guard.ok) { afsk_set_error("cannot select device %d", P->device); return AFSK_E_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
+    for (const Group &g : P->groups) {
+        DemodParams p;
+        p.samples = d_samples; p.caps = P->d_caps; p.clock = P->d_clock;
+        p.gcaps = g.d_caps; p.gtile_first = g.d_tile_first;
+        p.bits = P->d_bits; p.quiet = P->d_quiet;
+        p.ng = (int)g.caps.size(); p.total_items = g.tile_first.back();
+        p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.wt = g.wt;
+        p.stage_bytes = g.stage_bytes; p.stages = g.stages;
+        k_demod<<<g.grid, kDemodThreads, g.smem, st>>>(p);
+    }
+    k_frame<<<P->B, kFrameThreads, 0, st>>>(P->d_caps, P->d_clock, P->d_bits, P->d_quiet, d_out, d_res);
+    AFSK_CUDA(cudaGetLastError());
+    return AFSK_OK;
+}
+
+int afsk_rx_decode_host(int device, const int16_t *h_samples, const int64_t *h_offsets, int B, const int32_t *h_baud,
+                        const int32_t *h_amp_end, uint8_t *h_out, const int64_t *h_out_off, AfskRxResult *h_res)
+{
+    if (B < 0 || (B > 0 && (!h_samples || !h_offsets || !h_out || !h_out_off || !h_res))) return AFSK_E_ARG;
+    if (B == 0) return AFSK_OK;
+    AfskRxPlan *P = nullptr;
+    int rc = afsk_rx_plan_create(device, B, h_offsets, h_baud, h_amp_end, &P);
+    if (rc) return rc;
+    AfskDeviceGuard guard(device);
+    const int64_t total = h_offsets[B], base = h_offsets[0] & ~(int64_t)7;
+    const size_t sample_bytes = (size_t)(((total - base) * 2 + 15) & ~(int64_t)15) + 16;
+    int16_t *d_samples = nullptr; uint8_t *d_out = nullptr; AfskRxResult *d_res = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_samples, sample_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (size_t)P->out_off[B]);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_res, sizeof(AfskRxResult) * B);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_samples, h_samples + base, (size_t)(total - base) * 2, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) {
+        // the plan indexes samples from global sample 0: pass the shifted base pointer
+        rc = afsk_rx_decode(P, d_samples - base, d_out, d_res, nullptr);
+        if (rc == AFSK_OK) {
+            e = cudaMemcpyAsync(h_res, d_res, sizeof(AfskRxResult) * B, cudaMemcpyDeviceToHost, 0);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+            // compact copy-back: only the decoded bytes of each capture
+            std::vector<uint8_t> tmp;
+            if (e == cudaSuccess) {
+                tmp.resize((size_t)P->out_off[B]);
+                e = cudaMemcpy(tmp.data(), d_out, tmp.size(), cudaMemcpyDeviceToHost);
+            }
+            if (e == cudaSuccess) {
+                for (int c = 0; c < B; c++) {
+                    int64_t nb = h_res[c].nbytes, cap = h_out_off[c + 1] - h_out_off[c];
+                    if (nb > cap) { rc = AFSK_E_ARG; afsk_set_error("output capacity too small for capture %d", c); break; }
+                    if (nb > 0) memcpy(h_out + h_out_off[c], tmp.data() + P->out_off[c], (size_t)nb);
+                }
+            }
+        }
+    }
+    cudaFree(d_samples); cudaFree(d_out); cudaFree(d_res);
+    afsk_rx_plan_destroy(P);
+    if (e != cudaSuccess) { afsk_set_error("afsk_rx_decode_host: %s", cudaGetErrorString(e)); return AFSK_E_CUDA; }
+    return rc;
+}
+
+int afsk_rx_gate(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start, int amp_end,
+                 int64_t timeout_frames, int64_t *d_range, void *stream)
+{
+    if (S < 0 || (S > 0 && (!d_samples || !h_offsets || !d_range))) return AFSK_E_ARG;
+    if (S == 0) return AFSK_OK;
+    AfskDeviceGuard guard(device);
+    if (!guard.ok) return AFSK_E_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> first(S + 1, 0);
+    for (int s = 0; s < S; s++) first[s + 1] = first[s] + (h_offsets[s + 1] - h_offsets[s]) / AFSK_GATE_CHUNK;
+    const long long total = first[S];
+    int64_t *d_first = nullptr, *d_off = nullptr;
+    int32_t *d_amp = nullptr;
+    AFSK_CUDA(cudaMalloc((void **)&d_first, sizeof(int64_t) * (S + 1)));
+    AFSK_CUDA(cudaMalloc((void **)&d_off, sizeof(int64_t) * (S + 1)));
+    AFSK_CUDA(cudaMalloc((void **)&d_amp, sizeof(int32_t) * (total ? total : 1)));
+    AFSK_CUDA(cudaMemcpyAsync(d_first, first.data(), sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
+    AFSK_CUDA(cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
+    if (total > 0) {
+        const int wpb = 8;
+        k_gate_amp<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_samples, d_first, d_off, S, total, d_amp);
+    }
+    k_gate_scan<<<S, kFrameThreads, 0, st>>>(d_amp, d_first, amp_start, amp_end, timeout_frames, d_range);
+    AFSK_CUDA(cudaGetLastError());
+    AFSK_CUDA(cudaStreamSynchronize(st));     // host staging vectors go out of scope
+    cudaFree(d_first); cudaFree(d_off); cudaFree(d_amp);
+    return AFSK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// afsk_tx.cu — transmitter path of libafsk_b200.so (sm_100a).
+//
+// Replaces Transmitter.__getFrames (afskmodem.py:452-469: __bytesToBits :446-450, ECC.encode
+// :166-175, training cycles :457-458, terminator :460-462, one tone per coded bit :463-467,
+// 4800 zero frames :468) followed by SoundOutput.__convertFrames (:239-244, out[n] =
+// frames[n & ~1], odd trailing frame dropped) for B payloads.  Elementwise and write-bound:
+// each thread produces 16-byte vectors (8 samples) with coalesced 128-bit stores; the frame
+// value is recomputed from the payload byte (Hamming(7,4) codeword bit -> mark/space square
+// wave phase), nothing is staged in HBM.
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "afsk_common.cuh"
+
+namespace {
+
+constexpr int kSynthThreads = 256;
+constexpr int kVecPerThread = 4;
+constexpr int kChunkVecs = kSynthThreads * kVecPerThread;   // 1024 vectors = 8192 samples per CTA
+
+struct __align__(16) TxDesc {
+    int64_t pay_off;      // byte offset of the payload
+    int64_t pay_len;
+    int64_t out_off;      // sample offset of the capture (multiple of 8)
+    int64_t out_len;      // frames written by save(): (len(frames) & ~1)
+    int64_t sig_frames;   // frames before the zero tail = total_bits * bf
+    int64_t ts_bits;      // 2 * ts_cycles training bits (1,0,1,0,...)
+    int32_t bf;
+    int32_t pad;
+    int64_t chunk_first;  // first CTA chunk of this capture
+};
+
+// Hamming(7,4) generator (ECC.__M_GENERATOR :115-123): codeword bit r of nibble v, LSB = c0
+__device__ __forceinline__ uint32_t hamming74_encode(uint32_t v)
+{
+    const uint32_t d0 = (v >> 3) & 1u, d1 = (v >> 2) & 1u, d2 = (v >> 1) & 1u, d3 = v & 1u;
+    return (d0 ^ d1 ^ d3) | ((d0 ^ d2 ^ d3) << 1) | (d0 << 2) | ((d1 ^ d2 ^ d3) << 3) | (d1 << 4) | (d2 << 5) |
+           (d3 << 6);
+}
+
+__device__ __forceinline__ uint32_t tx_bit(long long b, const TxDesc &d, const uint8_t *__restrict__ pay)
+{
+    if (b < d.ts_bits) return (uint32_t)(~b & 1);            // training cycle = mark, space  :457-458
+    const long long t = b - d.ts_bits;
+    if (t < 4) return t == 0 ? 1u : 0u;                      // terminator mark, space x3     :460-462
+    const long long j = t - 4;                               // coded bit index
+    const long long g = j / 7;                               // nibble index, high nibble first :446-450
+    const uint32_t r = (uint32_t)(j - 7 * g);
+    const uint32_t byte = pay[d.pay_off + (g >> 1)];
+    const uint32_t nib = (g & 1) ? (byte & 15u) : (byte >> 4);
+    return (hamming74_encode(nib) >> r) & 1u;
+}
+
+// frame value at phase ph of a tone (Waveforms.getSpaceTone/getMarkTone :68-85), as 2 duplicated
+// int16 (SoundOutput.__convertFrames emits every even frame twice)
+__device__ __forceinline__ uint32_t tone_pair(uint32_t bit, int ph, int bf)
+{
+    const int q = bf >> 2, h = bf >> 1;
+    bool hi;
+    if (bit) hi = (ph < q) || (ph >= h && ph < h + q);       // mark : q HI, q LO, q HI, q LO
+    else hi = ph < h;                                        // space: h HI, h LO
+    return hi ? 0x7FFF7FFFu : 0x80008000u;
+}
+
+__global__ void __launch_bounds__(kSynthThreads) k_synth(const uint8_t *__restrict__ pay,
+                                                         const TxDesc *__restrict__ descs, int B,
+                                                         int16_t *__restrict__ out)
+{
+    // capture of this chunk
+    const long long chunk = blockIdx.x;
+    int a = 0, b = B;
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (descs[mid].chunk_first <= chunk) a = mid; else b = mid;
+    }
+    const TxDesc d = descs[a];
+    const long long nvec_cap = (d.out_len + 7) >> 3;          // vectors of this capture (last one zero padded)
+    const long long v0 = (chunk - d.chunk_first) * kChunkVecs;
+    uint4 *dst = reinterpret_cast<uint4 *>(out + d.out_off);
+#pragma unroll
+    for (int r = 0; r < kVecPerThread; r++) {
+        const long long vi = v0 + r * kSynthThreads + threadIdx.x;
+        if (vi >= nvec_cap) break;
+        const long long n0 = vi * 8;
+        long long bidx = n0 / d.bf;
+        int ph = (int)(n0 - bidx * d.bf);
+        uint32_t bit = (n0 < d.sig_frames) ? tx_bit(bidx, d, pay) : 0u;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long n = n0 + 2 * j;
+            uint32_t val = 0u;
+            if (n < d.out_len && n < d.sig_frames) val = tone_pair(bit, ph, d.bf);
+            w[j] = val;
+            ph += 2;
+            if (ph >= d.bf) {
+                ph -= d.bf;
+                bidx++;
+                if (n + 2 < d.sig_frames) bit = tx_bit(bidx, d, pay);
+            }
+        }
+        dst[vi] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+}  // namespace
+
+struct AfskTxPlan {
+    int device = 0;
+    int B = 0;
+    std::vector<TxDesc> descs;
+    std::vector<int64_t> out_off, out_len;
+    TxDesc *d_descs = nullptr;
+    int64_t total_chunks = 0;
+};
+
+extern "C" {
+
+int64_t afsk_tx_num_samples(int baud, int64_t ts_cycles, int64_t payload_bytes, const uint8_t *payload)
+{
+    int bf, ml, sl;
+    if (!afsk_tone_geometry(baud, &bf, &ml, &sl)) { afsk_set_error("Invalid baud rate."); return AFSK_E_BAUD; }
+    if (ts_cycles < 0) ts_cycles = 0;
+    int64_t frames = ts_cycles * (int64_t)(ml + sl) + ml + 3 * (int64_t)sl + AFSK_TAIL_FRAMES;
+    if (ml == sl) {
+        frames += payload_bytes * 14 * (int64_t)sl;
+    } else {
+        if (payload_bytes > 0 && !payload) { afsk_set_error("payload needed for unequal tone lengths"); return AFSK_E_ARG; }
+        for (int64_t i = 0; i < payload_bytes; i++) {
+            for (int half = 0; half < 2; half++) {
+                uint32_t v = half == 0 ? payload[i] >> 4 : payload[i] & 15u;
+                uint32_t d0 = (v >> 3) & 1u, d1 = (v >> 2) & 1u, d2 = (v >> 1) & 1u, d3 = v & 1u;
+                int ones = (int)((d0 ^ d1 ^ d3) + (d0 ^ d2 ^ d3) + d0 + (d1 ^ d2 ^ d3) + d1 + d2 + d3);
+                frames += (int64_t)ones * ml + (int64_t)(7 - ones) * sl;
+            }
+        }
+    }
+    return frames & ~(int64_t)1;      // SoundOutput.__convertFrames :241 drops an odd trailing frame
+}
+
+int afsk_tx_plan_create(int device, int B, const int64_t *h_pay_off, const int32_t *h_baud, const int64_t *h_ts_cycles,
+                        const uint8_t *h_payload, AfskTxPlan **plan_out)
+{
+    (void)h_payload;
+    if (!plan_out || B < 0 || (B > 0 && (!h_pay_off || !h_baud || !h_ts_cycles))) return AFSK_E_ARG;
+    AfskDeviceGuard guard(device);
+    if (!guard.ok) { afsk_set_error("cannot select device %d", device); return AFSK_E_CUDA; }
+    AfskTxPlan *P = new (std::nothrow) AfskTxPlan();
+    if (!P) return AFSK_E_ARG;
+    P->device = device;
+    P->B = B;
+    P->descs.resize(B);
+    P->out_off.assign(B + 1, 0);
+    P->out_len.assign(B, 0);
+    int64_t chunks = 0;
+    for (int c = 0; c < B; c++) {
+        int bf, ml, sl;
+        if (!afsk_tone_geometry(h_baud[c], &bf, &ml, &sl)) {
+            delete P; afsk_set_error("Invalid baud rate."); return AFSK_E_BAUD;
+        }
+        if (ml != sl) {
+            delete P;
+            afsk_set_error("baud %d has unequal mark/space tone lengths (%d/%d): not supported by the GPU synthesizer yet",
+                           h_baud[c], ml, sl);
+            return AFSK_E_UNSUPPORTED;
+        }
+        TxDesc &d = P->descs[c];
+        const int64_t ts = h_ts_cycles[c] < 0 ? 0 : h_ts_cycles[c];
+        d.pay_off = h_pay_off[c];
+        d.pay_len = h_pay_off[c + 1] - h_pay_off[c];
+        if (d.pay_len < 0) { delete P; afsk_set_error("payload offsets must be non-decreasing"); return AFSK_E_ARG; }
+        d.bf = bf; d.pad = 0;
+        d.ts_bits = 2 * ts;
+        d.sig_frames = (d.ts_bits + 4 + 14 * d.pay_len) * bf;
+        d.out_len = (d.sig_frames + AFSK_TAIL_FRAMES) & ~(int64_t)1;
+        d.out_off = P->out_off[c];
+        d.chunk_first = chunks;
+        const int64_t nvec = (d.out_len + 7) >> 3;
+        chunks += (nvec + kChunkVecs - 1) / kChunkVecs;
+        P->out_len[c] = d.out_len;
+        P->out_off[c + 1] = P->out_off[c] + nvec * 8;
+    }
+    P->total_chunks = chunks;
+    if (chunks > 0x7FFFFFFFLL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
+    cudaError_t e = cudaMalloc((void **)&P->d_descs, sizeof(TxDesc) * (B ? B : 1));
+    if (e == cudaSuccess && B) e = cudaMemcpy(P->d_descs, P->descs.data(), sizeof(TxDesc) * B, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        afsk_set_error("afsk_tx_plan_create: %s", cudaGetErrorString(e));
+        afsk_tx_plan_destroy(P);
+        return AFSK_E_CUDA;
+    }
+    *plan_out = P;
+    return AFSK_OK;
+}
+
+int afsk_tx_plan_destroy(AfskTxPlan *P)
+{
+    if (!P) return AFSK_OK;
+    AfskDeviceGuard guard(P->device);
+    cudaFree(P->d_descs);
+    delete P;
+    return AFSK_OK;
+}
+
+int afsk_tx_plan_out_offsets(const AfskTxPlan *P, const int64_t **h_out_off, const int64_t **h_out_len)
+{
+    if (!P) return AFSK_E_ARG;
+    if (h_out_off) *h_out_off = P->out_off.data();
+    if (h_out_len) *h_out_len = P->out_len.data();
+    return AFSK_OK;
+}
+
+int afsk_tx_synth(AfskTxPlan *P, const uint8_t *d_payload, int16_t *d_out, void *stream)
+{
+    if (!P || (P->B > 0 && !d_out)) return AFSK_E_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) { afsk_set_error("afsk_tx_synth: d_out must be 16-byte aligned"); return AFSK_E_ARG; }
+    if (P->B == 0 || P->total_chunks == 0) return AFSK_OK;
+    AfskDeviceGuard guard(P->device);
+    if (!guard.ok) return AFSK_E_CUDA;
+    k_synth<<<(unsigned)P->total_chunks, kSynthThreads, 0, (cudaStream_t)stream>>>(d_payload, P->d_descs, P->B, d_out);
+    AFSK_CUDA(cudaGetLastError());
+    return AFSK_OK;
+}
+
+int afsk_tx_synth_host(int device, const uint8_t *h_payload, const int64_t *h_pay_off, int B, const int32_t *h_baud,
+                       const int64_t *h_ts_cycles, int16_t *h_out, const int64_t *h_out_off)
+{
+    if (B < 0 || (B > 0 && (!h_pay_off || !h_out || !h_out_off))) return AFSK_E_ARG;
+    if (B == 0) return AFSK_OK;
+    AfskTxPlan *P = nullptr;
+    int rc = afsk_tx_plan_create(device, B, h_pay_off, h_baud, h_ts_cycles, h_payload, &P);
+    if (rc) return rc;
+    AfskDeviceGuard guard(device);
+    const int64_t pay_bytes = h_pay_off[B];
+    uint8_t *d_pay = nullptr; int16_t *d_out = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_pay, (size_t)(pay_bytes ? pay_bytes : 16));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (size_t)(P->out_off[B] ? P->out_off[B] : 8) * 2);
+    if (e == cudaSuccess && pay_bytes) e = cudaMemcpy(d_pay, h_payload, (size_t)pay_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = afsk_tx_synth(P, d_pay, d_out, nullptr);
+        for (int c = 0; c < B && rc == AFSK_OK && e == cudaSuccess; c++) {
+            if (h_out_off[c + 1] - h_out_off[c] < P->out_len[c]) { rc = AFSK_E_ARG; afsk_set_error("output capacity too small for capture %d", c); break; }
+            if (P->out_len[c])
+                e = cudaMemcpy(h_out + h_out_off[c], d_out + P->out_off[c], (size_t)P->out_len[c] * 2, cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFree(d_pay); cudaFree(d_out);
+    afsk_tx_plan_destroy(P);
+    if (e != cudaSuccess) { afsk_set_error("afsk_tx_synth_host: %s", cudaGetErrorString(e)); return AFSK_E_CUDA; }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,513 @@
+"""Host-side mirror of the reference's class API (afskmodem.py:19-61 Log, :66-107 Waveforms,
+:114-175 ECC, :274-430 Receiver, :436-484 Transmitter) over the CUDA core.
+
+Same names, argument meaning, log text, return types and error behaviour as the reference on the
+file path (``load``/``save``); batch entry points (``decode_batch``, ``load_batch``,
+``encode_batch``, ``save_batch``) are additions.  All signal processing runs in
+``libafsk_b200.so``; this module only validates arguments, moves bytes and formats results.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import wave
+from datetime import datetime
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import AfskError, DeviceBuffer
+
+# Log level (0: Debug, 1: Info, 2: Warn, 3: Error, 4: Fatal) — same global as afskmodem.py:14.
+# The package-level ``afskmodem_b200.LOG_LEVEL`` is the one users set; see __init__.py.
+_LEVEL_TAGS = {1: " [ INFO ]  ", 2: " [ WARN ]  ", 3: " [ ERROR ] ", 4: " [ FATAL ] "}
+
+
+def _log_level() -> int:
+    import afskmodem_b200
+    return afskmodem_b200.LOG_LEVEL
+
+
+class Log:
+    """Timestamped print logger with the reference's line format (afskmodem.py:19-61)."""
+
+    def __init__(self, class_name: str):
+        self._name = class_name
+
+    def _emit(self, level: int, message: str) -> None:
+        if level >= _log_level():
+            print(datetime.now().strftime("%Y-%m-%d %H:%M:%S") + _LEVEL_TAGS.get(level, " [ DEBUG ] ")
+                  + self._name.ljust(24) + ": " + message)
+
+    def debug(self, message: str) -> None:
+        self._emit(0, message)
+
+    def info(self, message: str) -> None:
+        self._emit(1, message)
+
+    def warn(self, message: str) -> None:
+        self._emit(2, message)
+
+    def error(self, message: str) -> None:
+        self._emit(3, message)
+
+    def fatal(self, message: str) -> None:
+        self._emit(4, message)
+
+
+class Waveforms:
+    """Tone tables and the two waveform metrics (afskmodem.py:66-107), host utilities.
+
+    The receiver/transmitter do not call these (the CUDA kernels use closed forms); they exist so
+    code written against the reference's ``Waveforms`` keeps working.
+    """
+
+    @staticmethod
+    def getSpaceTone(baud_rate: int) -> list[int]:
+        if 48000 % baud_rate != 0:
+            raise Exception("Invalid baud rate.")
+        half = int((48000 / baud_rate) / 2)
+        return [32767] * half + [-32768] * half
+
+    @staticmethod
+    def getMarkTone(baud_rate: int) -> list[int]:
+        if 48000 % baud_rate != 0:
+            raise Exception("Invalid baud rate.")
+        return Waveforms.getSpaceTone(baud_rate * 2) * 2
+
+    @staticmethod
+    def getTrainingCycle(baud_rate: int) -> list[int]:
+        return Waveforms.getMarkTone(baud_rate) + Waveforms.getSpaceTone(baud_rate)
+
+    @staticmethod
+    def getAmplitude(frames) -> int:
+        a = np.asarray(frames, dtype=np.int64)
+        return int(int(np.abs(a).sum()) / len(a))
+
+    @staticmethod
+    def getDiff(a, b) -> int:
+        if len(a) != len(b):
+            raise Exception("Comparing two waveforms of different lengths.")
+        d = np.asarray(a, dtype=np.int64) - np.asarray(b, dtype=np.int64)
+        return int(int(np.abs(d).sum()) / len(a))
+
+
+class ECC:
+    """Hamming(7,4) on '0'/'1' strings (afskmodem.py:114-175), host utility (table driven)."""
+
+    @staticmethod
+    def _codeword(nib: int) -> str:
+        d0, d1, d2, d3 = (nib >> 3) & 1, (nib >> 2) & 1, (nib >> 1) & 1, nib & 1
+        return "".join(str(b) for b in (d0 ^ d1 ^ d3, d0 ^ d2 ^ d3, d0, d1 ^ d2 ^ d3, d1, d2, d3))
+
+    @staticmethod
+    def encode(bits: str) -> str:
+        table = [ECC._codeword(n) for n in range(16)]
+        return "".join(table[int("".join("0" if ch == "0" else "1" for ch in bits[i:i + 4]), 2)]
+                       for i in range(0, len(bits) - 3, 4))
+
+    @staticmethod
+    def decode(bits: str) -> str:
+        out = []
+        for i in range(0, len(bits) - 6, 7):
+            c = [0 if ch == "0" else 1 for ch in bits[i:i + 7]]
+            e = (c[0] ^ c[2] ^ c[4] ^ c[6]) + 2 * (c[1] ^ c[2] ^ c[5] ^ c[6]) + 4 * (c[3] ^ c[4] ^ c[5] ^ c[6])
+            if e:
+                c[e - 1] ^= 1
+            out.append("%d%d%d%d" % (c[2], c[4], c[5], c[6]))
+        return "".join(out)
+
+
+def _check_baud(baud_rate) -> int:
+    """Constructor-time validation with the reference's exceptions (afskmodem.py:69-70, 81-83)."""
+    Waveforms.getSpaceTone(baud_rate)      # raises Exception("Invalid baud rate.") / ZeroDivisionError
+    Waveforms.getMarkTone(baud_rate)
+    if int(baud_rate) != baud_rate:
+        raise Exception("Invalid baud rate.")
+    return int(baud_rate)
+
+
+def _as_int_threshold(t) -> int:
+    # floor(mean) < t  <=>  floor(mean) < ceil(t) for real t
+    return int(np.ceil(t))
+
+
+# ------------------------------------------------------------------------------ receiver ----
+class RxBatch:
+    """Decoded batch: per-capture stage integers (the reference's debug-log values) and payloads."""
+
+    def __init__(self, results: np.ndarray, blob: np.ndarray, out_off: np.ndarray):
+        self.results = results            # structured: status, clock, train_end, nbits, nbytes
+        self.blob = blob                  # uint8, capacity layout
+        self.out_off = out_off            # int64 [B+1]
+
+    def __len__(self) -> int:
+        return len(self.results)
+
+    status = property(lambda self: self.results["status"])
+    clock = property(lambda self: self.results["clock"])
+    train_end = property(lambda self: self.results["train_end"])
+    nbits = property(lambda self: self.results["nbits"])
+    nbytes = property(lambda self: self.results["nbytes"])
+
+    def payload(self, i: int) -> bytes:
+        o = int(self.out_off[i])
+        return self.blob[o:o + int(self.results["nbytes"][i])].tobytes()
+
+    def payloads(self) -> list[bytes]:
+        return [self.payload(i) for i in range(len(self))]
+
+    def total_payload_bytes(self) -> int:
+        return int(self.results["nbytes"].sum())
+
+
+class RxSession:
+    """A plan plus device buffers for one batch layout on one GPU.
+
+    ``upload`` (H2D) / ``run`` (kernels, async on ``stream``) / ``download`` (D2H) are separate so
+    that callers can keep samples resident in HBM (bench ``value``) or time the whole call (``e2e``).
+    ``d_samples`` may be an external device pointer (e.g. ``torch.Tensor.data_ptr()``).
+    """
+
+    def __init__(self, offsets, baud, amp_end, device: int = 0):
+        _cabi.require_device(device)
+        L = _cabi.lib()
+        self.device = device
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.B = len(self.offsets) - 1
+        self.baud = np.ascontiguousarray(np.broadcast_to(np.asarray(baud, dtype=np.int32), (self.B,)))
+        self.amp_end = np.ascontiguousarray(np.broadcast_to(np.asarray(amp_end, dtype=np.int32), (self.B,)))
+        plan = C.c_void_p()
+        _cabi.check(L.afsk_rx_plan_create(device, self.B, _cabi.ptr(self.offsets, C.c_int64),
+                                          _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
+                                          C.byref(plan)))
+        self.plan = plan
+        po = C.POINTER(C.c_int64)()
+        _cabi.check(L.afsk_rx_plan_out_offsets(plan, C.byref(po)))
+        self.out_off = np.ctypeslib.as_array(po, shape=(self.B + 1,)).copy()
+        n = C.c_int(0)
+        _cabi.check(L.afsk_rx_plan_launches(plan, C.byref(n)))
+        self.launches = n.value
+        self.total_samples = int(self.offsets[-1])
+        self.d_out = DeviceBuffer(device, int(self.out_off[-1]))
+        self.d_res = DeviceBuffer(device, 32 * max(self.B, 1))
+        self.d_samples = None
+        self._ext_ptr = None
+
+    def close(self):
+        if getattr(self, "plan", None):
+            _cabi.lib().afsk_rx_plan_destroy(self.plan)
+            self.plan = None
+        for b in ("d_out", "d_res", "d_samples"):
+            buf = getattr(self, b, None)
+            if buf is not None:
+                buf.close()
+
+    __del__ = close
+
+    def upload(self, samples: np.ndarray, stream=None):
+        samples = np.ascontiguousarray(samples, dtype=np.int16)
+        assert len(samples) >= self.total_samples
+        if self.d_samples is None:
+            self.d_samples = DeviceBuffer(self.device, (self.total_samples * 2 + 15) // 16 * 16 + 16)
+        self.d_samples.upload(samples[:self.total_samples], stream)
+        self._ext_ptr = None
+
+    def bind(self, device_ptr: int):
+        """Use caller-owned device samples (16-byte aligned, padded to 16 bytes past the end)."""
+        self._ext_ptr = int(device_ptr)
+
+    def run(self, stream=None):
+        p = self._ext_ptr if self._ext_ptr is not None else self.d_samples.ptr
+        _cabi.check(_cabi.lib().afsk_rx_decode(self.plan, C.c_void_p(p), C.c_void_p(self.d_out.ptr),
+                                               C.c_void_p(self.d_res.ptr), C.c_void_p(stream or 0)))
+
+    def download(self, stream=None, res_host: np.ndarray | None = None, blob_host: np.ndarray | None = None) -> RxBatch:
+        res = res_host if res_host is not None else np.zeros(self.B, dtype=_cabi.RX_RESULT_DTYPE)
+        blob = blob_host if blob_host is not None else np.zeros(int(self.out_off[-1]), dtype=np.uint8)
+        if self.B:
+            self.d_res.download(res, stream)
+            self.d_out.download(blob, stream)
+        _cabi.stream_sync(self.device, stream)
+        return RxBatch(res, blob, self.out_off)
+
+    def planes(self, capture: int):
+        """(bits, quiet) numpy bool arrays of capture's windows after a run — stage-level parity."""
+        L = _cabi.lib()
+        pb, pq, mw = C.c_void_p(), C.c_void_p(), C.c_int64(0)
+        _cabi.check(L.afsk_rx_plan_planes(self.plan, capture, C.byref(pb), C.byref(pq), C.byref(mw)))
+        nw = (mw.value + 31) // 32
+        out = []
+        for p in (pb, pq):
+            words = np.zeros(max(nw, 1), dtype=np.uint32)
+            if nw:
+                _cabi.check(L.afsk_memcpy_d2h(self.device, C.c_void_p(words.ctypes.data), p, nw * 4, None))
+            _cabi.stream_sync(self.device)
+            out.append(np.unpackbits(words.view(np.uint8), bitorder="little")[:mw.value].astype(bool))
+        return out[0], out[1]
+
+
+def _concat(captures):
+    """list of int16 arrays -> (concatenated samples with each capture 16-byte aligned, offsets)."""
+    lens = np.array([len(c) for c in captures], dtype=np.int64)
+    samples = np.concatenate([np.asarray(c, dtype=np.int16) for c in captures]) if len(captures) else \
+        np.zeros(0, np.int16)
+    offsets = np.zeros(len(captures) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    return samples, offsets
+
+
+def read_wav_frames(filename: str) -> np.ndarray:
+    """SoundInput.loadFromFile (afskmodem.py:213-217): all frame bytes, paired little-endian signed,
+    whatever the header says about channels/width (the reference does not check either)."""
+    with wave.open(filename, "rb") as f:
+        raw = f.readframes(f.getnframes())
+    return np.frombuffer(raw, dtype="<i2", count=len(raw) // 2)
+
+
+class Receiver:
+    """Receiver(baud_rate, amp_start_threshold, amp_end_threshold) — afskmodem.py:274-430."""
+
+    def __init__(self, baud_rate: int = 1200, amp_start_threshold: int = 18000,
+                 amp_end_threshold: int = 14000, device: int = 0):
+        self._bit_frames = int(48000 / baud_rate)                # :277
+        self._baud = _check_baud(baud_rate)                      # raises like :280-282
+        self._amp_start = amp_start_threshold                    # live path only (:306)
+        self._amp_end = amp_end_threshold
+        self._device = device
+        self._log = Log("afskmodem.Receiver")
+
+    # -- batch API -------------------------------------------------------------------------
+    def decode_batch(self, samples, offsets=None, device: int | None = None) -> RxBatch:
+        """Decode B captures.  ``samples``: list of int16 arrays, or one concatenated int16 array
+        with ``offsets`` (B+1, in samples).  Raises the reference's exceptions only through
+        ``to_python``; statuses < 0 mark captures on which ``load`` would raise."""
+        if offsets is None:
+            samples, offsets = _concat(samples)
+        dev = self._device if device is None else device
+        s = RxSession(offsets, self._baud, _as_int_threshold(self._amp_end), dev)
+        try:
+            s.upload(samples)
+            s.run()
+            return s.download()
+        finally:
+            s.close()
+
+    def to_python(self, batch: RxBatch, i: int, string: bool = True, log: bool = True):
+        """Capture i of a batch as ``load`` would have returned it (F8 return-type rules), with the
+        reference's log lines; raises what ``load`` raises."""
+        st = int(batch.status[i])
+        lg = self._log if log else _NULL_LOG
+        if st == _cabi.ST_EXC_WAVELEN:
+            raise Exception("Comparing two waveforms of different lengths.")       # :102-103
+        if st == _cabi.ST_EXC_INDEX:
+            raise IndexError("list index out of range")                            # :332
+        if st == _cabi.ST_EXC_BAUD:
+            raise Exception("Invalid baud rate.")
+        if st == _cabi.ST_NO_CLOCK:
+            lg.warn("Failed to recover clock from received signal.")               # :324
+            lg.warn("No data.")                                                    # :423
+            return b""
+        lg.debug("Recovered clock. (frame " + str(int(batch.clock[i])) + ")")       # :338
+        lg.debug("Training sequence terminated on frame " + str(int(batch.train_end[i])))   # :368
+        lg.debug("Decoded " + str(int(batch.nbits[i])) + " bits. (including ECC)")  # :380
+        if st == _cabi.ST_NO_DATA:
+            lg.warn("No data.")
+            return b""
+        data = batch.payload(i)
+        lg.debug("Decoded " + str(len(data)) + " bytes.")                          # :427
+        if string:
+            return data.decode("utf-8")                                            # :428-429
+        return data
+
+    def load_batch(self, filenames, string: bool = True, errors: str = "raise"):
+        """``load`` over many files in one GPU batch.  errors="return" puts the exception object in
+        the list instead of raising at the first failing capture."""
+        caps = [read_wav_frames(f) for f in filenames]
+        batch = self.decode_batch(caps)
+        out = []
+        for i in range(len(caps)):
+            try:
+                out.append(self.to_python(batch, i, string))
+            except Exception as e:  # noqa: BLE001 - mirrors whatever load raises
+                if errors == "raise":
+                    raise
+                out.append(e)
+        return out
+
+    # -- reference API ---------------------------------------------------------------------
+    def load(self, filename: str, string: bool = True) -> bytes | str:
+        """Reads signal from a file, decodes it, then returns it (or fails) — afskmodem.py:420-430."""
+        frames = read_wav_frames(filename)
+        return self.to_python(self.decode_batch([frames]), 0, string)
+
+    read = load          # README.md:94 name
+
+    def listen_gate(self, stream_samples, timeout: float, device: int | None = None):
+        """Receiver.__listen (:299-319) over recorded streams → list of (recorded, start, end)."""
+        streams = stream_samples if isinstance(stream_samples, (list, tuple)) else [stream_samples]
+        samples, offsets = _concat(streams)
+        dev = self._device if device is None else device
+        _cabi.require_device(dev)
+        d_s = DeviceBuffer(dev, len(samples) * 2 + 32)
+        d_r = DeviceBuffer(dev, 24 * len(streams))
+        try:
+            d_s.upload(samples)
+            _cabi.check(_cabi.lib().afsk_rx_gate(dev, C.c_void_p(d_s.ptr), _cabi.ptr(offsets, C.c_int64),
+                                                 len(streams), int(np.floor(self._amp_start)),
+                                                 _as_int_threshold(self._amp_end), int(timeout * 48000),
+                                                 C.c_void_p(d_r.ptr), None))
+            r = np.zeros((len(streams), 3), dtype=np.int64)
+            d_r.download(r)
+            _cabi.stream_sync(dev)
+        finally:
+            d_s.close()
+            d_r.close()
+        return [(bool(a), int(b), int(c)) for a, b, c in r]
+
+    def receive_recording(self, stream_samples, timeout: float, string: bool = True) -> bytes | str:
+        """``receive`` (:402-417) with the audio device replaced by a recorded int16 stream."""
+        self._log.info("Listening...")
+        rec, a, b = self.listen_gate(stream_samples, timeout)[0]
+        if not rec:
+            self._log.warn("Timed out.")
+            return b""
+        self._log.debug("Recording started")
+        self._log.debug("Recording finished")
+        frames = np.asarray(stream_samples, dtype=np.int16)[a:b]
+        return self.to_python(self.decode_batch([frames]), 0, string)
+
+    def receive(self, timeout: float, string: bool = True) -> bytes | str:
+        """Live microphone path (:402-417).  Needs an audio device; out of scope for the GPU core —
+        record with any tool and use ``receive_recording`` / ``load``."""
+        raise RuntimeError("afskmodem_b200 has no live audio input; use receive_recording() or load()")
+
+
+class _NullLog:
+    def debug(self, m): pass
+    def info(self, m): pass
+    def warn(self, m): pass
+
+
+_NULL_LOG = _NullLog()
+
+
+# --------------------------------------------------------------------------- transmitter ----
+class TxBatch:
+    def __init__(self, samples: np.ndarray, out_off: np.ndarray, out_len: np.ndarray):
+        self.samples, self.out_off, self.out_len = samples, out_off, out_len
+
+    def __len__(self) -> int:
+        return len(self.out_len)
+
+    def frames(self, i: int) -> np.ndarray:
+        o = int(self.out_off[i])
+        return self.samples[o:o + int(self.out_len[i])]
+
+
+class TxSession:
+    """Plan + device buffers for one batch of payloads on one GPU (see RxSession)."""
+
+    def __init__(self, payloads, baud, ts_cycles, device: int = 0):
+        _cabi.require_device(device)
+        L = _cabi.lib()
+        self.device = device
+        self.B = len(payloads)
+        lens = np.array([len(p) for p in payloads], dtype=np.int64)
+        self.pay_off = np.zeros(self.B + 1, dtype=np.int64)
+        np.cumsum(lens, out=self.pay_off[1:])
+        self.payload = np.frombuffer(b"".join(bytes(p) for p in payloads), dtype=np.uint8).copy() \
+            if self.pay_off[-1] else np.zeros(1, dtype=np.uint8)
+        self.baud = np.ascontiguousarray(np.broadcast_to(np.asarray(baud, dtype=np.int32), (self.B,)))
+        self.ts = np.ascontiguousarray(np.broadcast_to(np.asarray(ts_cycles, dtype=np.int64), (self.B,)))
+        plan = C.c_void_p()
+        rc = L.afsk_tx_plan_create(device, self.B, _cabi.ptr(self.pay_off, C.c_int64), _cabi.ptr(self.baud, C.c_int32),
+                                   _cabi.ptr(self.ts, C.c_int64), _cabi.ptr(self.payload, C.c_uint8), C.byref(plan))
+        if rc == _cabi.AFSK_E_BAUD:
+            raise Exception("Invalid baud rate.")
+        if rc == _cabi.AFSK_E_UNSUPPORTED:
+            raise NotImplementedError(L.afsk_last_error().decode())
+        _cabi.check(rc)
+        self.plan = plan
+        po, pl = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        _cabi.check(L.afsk_tx_plan_out_offsets(plan, C.byref(po), C.byref(pl)))
+        self.out_off = np.ctypeslib.as_array(po, shape=(self.B + 1,)).copy()
+        self.out_len = np.ctypeslib.as_array(pl, shape=(max(self.B, 1),)).copy()[:self.B]
+        self.d_pay = DeviceBuffer(device, len(self.payload))
+        self.d_out = DeviceBuffer(device, int(self.out_off[-1]) * 2)
+
+    def close(self):
+        if getattr(self, "plan", None):
+            _cabi.lib().afsk_tx_plan_destroy(self.plan)
+            self.plan = None
+        for b in ("d_pay", "d_out"):
+            buf = getattr(self, b, None)
+            if buf is not None:
+                buf.close()
+
+    __del__ = close
+
+    def upload(self, stream=None):
+        self.d_pay.upload(self.payload, stream)
+
+    def run(self, stream=None):
+        _cabi.check(_cabi.lib().afsk_tx_synth(self.plan, C.c_void_p(self.d_pay.ptr), C.c_void_p(self.d_out.ptr),
+                                              C.c_void_p(stream or 0)))
+
+    def download(self, stream=None, host: np.ndarray | None = None) -> TxBatch:
+        out = host if host is not None else np.zeros(int(self.out_off[-1]), dtype=np.int16)
+        if len(out):
+            self.d_out.download(out, stream)
+        _cabi.stream_sync(self.device, stream)
+        return TxBatch(out, self.out_off, self.out_len)
+
+
+def write_wav_frames(filename: str, frames: np.ndarray) -> None:
+    """SoundOutput.writeToFile (afskmodem.py:256-263): 1 channel, 16 bit, 48 kHz."""
+    with wave.open(filename, "wb") as f:
+        f.setnchannels(1)
+        f.setsampwidth(2)
+        f.setframerate(48000)
+        f.writeframes(np.ascontiguousarray(frames, dtype="<i2").tobytes())
+
+
+class Transmitter:
+    """Transmitter(baud_rate, training_time) — afskmodem.py:436-484."""
+
+    def __init__(self, baud_rate: int = 1200, training_time: float = 0.5, device: int = 0,
+                 training_sequence_time: float | None = None):
+        if training_sequence_time is not None:                   # README.md:107 spelling
+            training_time = training_sequence_time
+        self._ts_cycles = int(baud_rate * training_time / 2)     # :438
+        self._baud = _check_baud(baud_rate)                      # raises like :439-441
+        self._device = device
+        self._log = Log("afskmodem.Transmitter")
+
+    @staticmethod
+    def _as_bytes(data) -> bytes:
+        return data.encode("utf-8") if isinstance(data, str) else bytes(data)     # :473-474, :482-483
+
+    def encode_batch(self, payloads, device: int | None = None) -> TxBatch:
+        """Frames ``save`` would write for each payload (str or bytes), synthesized on the GPU."""
+        s = TxSession([self._as_bytes(p) for p in payloads], self._baud, self._ts_cycles,
+                      self._device if device is None else device)
+        try:
+            s.upload()
+            s.run()
+            return s.download()
+        finally:
+            s.close()
+
+    def save_batch(self, payloads, filenames) -> None:
+        batch = self.encode_batch(payloads)
+        for i, fn in enumerate(filenames):
+            write_wav_frames(fn, batch.frames(i))
+
+    def save(self, data: str | bytes, filename: str):
+        """Transmits the given data, saving the resulting audio to a .wav file — afskmodem.py:481-484."""
+        write_wav_frames(filename, self.encode_batch([data]).frames(0))
+
+    write = save         # README.md:119 name
+
+    def transmit(self, data: str | bytes):
+        """Live speaker path (:472-478).  Needs an audio device; out of scope — use ``save``."""
+        raise RuntimeError("afskmodem_b200 has no live audio output; use save()")

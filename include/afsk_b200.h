@@ -1,0 +1,155 @@
+/*
+ * afsk_b200.h — C ABI of libafsk_b200.so, the B200 (sm_100a) batch AFSK modem core.
+ *
+ * The reference (lavajuno/afskmodem, one pure-Python file) has no FFI/plugin interface; its
+ * boundary is the Python class API (afskmodem.py:275-276 Receiver, :420 load, :437 Transmitter,
+ * :481 save).  This header is the C surface a binding for that path needs: plain pointers and
+ * sizes, no torch types.  Each entry point names the reference function(s) it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (AFSK_E_*); afsk_last_error() gives text
+ *     (thread-local).  Nothing throws.  There is NO CPU fallback: without a CUDA device every
+ *     compute entry point returns AFSK_E_CUDA.
+ *   - device pointers are caller-owned; `stream` is a cudaStream_t passed as void* (NULL =
+ *     default stream).  Calls taking a stream are asynchronous on it.
+ *   - sample buffers are int16 little-endian, 48 kHz mono, captures concatenated; offsets are in
+ *     samples (CSR: capture c = [off[c], off[c+1]) ).  The device sample pointer must be 16-byte
+ *     aligned and the allocation must extend to the next 16-byte boundary past off[B].
+ *   - one process/thread per GPU; a plan belongs to the device it was created on.
+ */
+#ifndef AFSK_B200_H
+#define AFSK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFSK_ABI_VERSION 1
+
+/* return codes */
+#define AFSK_OK 0
+#define AFSK_E_ARG (-1)     /* bad argument (null, misaligned, negative size ...) */
+#define AFSK_E_CUDA (-2)    /* CUDA runtime error / no device                      */
+#define AFSK_E_BAUD (-3)    /* Exception("Invalid baud rate.")  afskmodem.py:69-70,81-82 */
+#define AFSK_E_UNSUPPORTED (-4)
+
+/* per-capture decode status (AfskRxResult.status) */
+#define AFSK_ST_OK 0            /* >= 1 coded bit decoded                                      */
+#define AFSK_ST_NO_CLOCK 1      /* len(frames) < 4096: "Failed to recover clock" :323-325      */
+#define AFSK_ST_NO_DATA 2       /* clock found but 0 bits: "No data." :422-424                 */
+#define AFSK_ST_EXC_WAVELEN (-1)/* Exception("Comparing two waveforms of different lengths.")  */
+#define AFSK_ST_EXC_INDEX (-2)  /* IndexError at scan_diffs[0] :332 (2*bit_frames >= 4096)      */
+#define AFSK_ST_EXC_BAUD (-3)   /* constructor would raise "Invalid baud rate."                */
+
+/* One per capture; the four integers are the reference's debug-log stage values
+ * (afskmodem.py:338, :368, :380, :427). */
+typedef struct AfskRxResult {
+    int32_t status;
+    int32_t clock;       /* -1 when no clock */
+    int64_t train_end;   /* -1 when no clock */
+    int64_t nbits;
+    int64_t nbytes;
+} AfskRxResult;
+
+typedef struct AfskRxPlan AfskRxPlan;
+typedef struct AfskTxPlan AfskTxPlan;
+
+/* ---------------------------------------------------------------- library / device ---- */
+int afsk_abi_version(void);
+const char *afsk_last_error(void);
+int afsk_device_count(int *count);
+/* SM count, global memory bytes, compute capability major*10+minor of `device` */
+int afsk_device_info(int device, int *sm_count, size_t *mem_bytes, int *cc);
+
+/* minimal memory / stream helpers so a host binding needs no other CUDA wrapper */
+int afsk_malloc(int device, size_t bytes, void **dptr);
+int afsk_free(int device, void *dptr);
+int afsk_host_alloc(size_t bytes, void **hptr);           /* pinned */
+int afsk_host_free(void *hptr);
+int afsk_memcpy_h2d(int device, void *dst, const void *src, size_t bytes, void *stream);
+int afsk_memcpy_d2h(int device, void *dst, const void *src, size_t bytes, void *stream);
+int afsk_memset(int device, void *dst, int value, size_t bytes, void *stream);
+int afsk_stream_create(int device, void **stream);
+int afsk_stream_destroy(int device, void *stream);
+int afsk_stream_sync(int device, void *stream);
+
+/* ---------------------------------------------------------------- tone tables ---------- */
+/* Waveforms.getSpaceTone / getMarkTone lengths (afskmodem.py:68-85) and Receiver.__bit_frames
+ * (:277).  Returns AFSK_E_BAUD where the reference constructor raises. */
+int afsk_tone_lengths(int baud, int *bit_frames, int *mark_len, int *space_len);
+
+/* ---------------------------------------------------------------- receiver ------------- */
+/*
+ * Replaces Receiver.load's compute (afskmodem.py:420-430): __decodeBits :354-381
+ * (__recoverClockIndex :322-339, __decodeBit :342-351 with __amplify :287-296 and
+ * Waveforms.getDiff/getAmplitude :94-107, __scanTraining :386-390), ECC.decode :154-163 and
+ * __bitsToBytes :393-399, for B independent captures.
+ *
+ * h_offsets[B+1] (samples), h_baud[B], h_amp_end[B] are HOST arrays describing the batch
+ * (amp_end = Receiver's amp_end_threshold; amp_start is unused on the file path, :375 vs :306).
+ * A plan holds the device-side descriptors and scratch (bit planes, clock indices).
+ */
+int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32_t *h_baud,
+                        const int32_t *h_amp_end, AfskRxPlan **plan);
+int afsk_rx_plan_destroy(AfskRxPlan *plan);
+/* capacity offsets (bytes, B+1 entries, host memory owned by the plan) of the decoded output */
+int afsk_rx_plan_out_offsets(const AfskRxPlan *plan, const int64_t **h_out_off);
+/* number of kernel launches one afsk_rx_decode issues for this plan */
+int afsk_rx_plan_launches(const AfskRxPlan *plan, int *launches);
+/*
+ * d_samples: device int16[h_offsets[B]] ; d_out: device bytes[h_out_off[B]] ; d_res: device
+ * AfskRxResult[B].  Capture c's payload is d_out[h_out_off[c] .. + d_res[c].nbytes).
+ */
+int afsk_rx_decode(AfskRxPlan *plan, const int16_t *d_samples, uint8_t *d_out, AfskRxResult *d_res,
+                   void *stream);
+/* raw coded bits / quiet flags of capture c after a decode, packed LSB-first, for diagnostics
+ * and stage-level parity tests: window k of capture c is bit (k & 31) of word k >> 5. */
+int afsk_rx_plan_planes(const AfskRxPlan *plan, int capture, const uint32_t **d_bits,
+                        const uint32_t **d_quiet, int64_t *max_windows);
+/*
+ * Host-buffer convenience (what a drop-in Receiver.load calls): H2D, decode, D2H on `device`.
+ * h_out_off[B+1] are capacity offsets into h_out (use afsk_rx_out_capacity per capture).
+ */
+int afsk_rx_decode_host(int device, const int16_t *h_samples, const int64_t *h_offsets, int B,
+                        const int32_t *h_baud, const int32_t *h_amp_end, uint8_t *h_out,
+                        const int64_t *h_out_off, AfskRxResult *h_res);
+/* upper bound on decoded bytes of a capture of n samples at `baud` */
+int64_t afsk_rx_out_capacity(int64_t n_samples, int baud);
+
+/*
+ * Receiver.__listen gate arithmetic (afskmodem.py:299-319) over S recorded streams: chunk 0 is
+ * discarded, the first 2048-frame chunk with floor(sum|x|/2048) > amp_start opens the recording,
+ * it extends through the first chunk with amplitude < amp_end.  h_offsets[S+1] in samples.
+ * d_range receives int64 {recorded(0/1), start, end} per stream.  Finite-stream conventions:
+ * exhausted before opening → recorded = 0; exhausted before closing → end = last full chunk.
+ */
+int afsk_rx_gate(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start,
+                 int amp_end, int64_t timeout_frames, int64_t *d_range, void *stream);
+
+/* ---------------------------------------------------------------- transmitter ---------- */
+/* frames Transmitter.save writes for a payload of n bytes (afskmodem.py:452-469 then :239-244).
+ * Needs the payload only when mark/space tone lengths differ (e.g. 4800 baud); pass NULL else. */
+int64_t afsk_tx_num_samples(int baud, int64_t ts_cycles, int64_t payload_bytes, const uint8_t *payload);
+/*
+ * Replaces Transmitter.__getFrames (:452-469: __bytesToBits :446-450, ECC.encode :166-175,
+ * training sequence, terminator, 4800-frame tail) + SoundOutput.__convertFrames (:239-244) for
+ * B payloads.  h_pay_off[B+1] bytes; h_baud[B]; h_ts_cycles[B] = int(baud*training_time/2) (:438).
+ */
+int afsk_tx_plan_create(int device, int B, const int64_t *h_pay_off, const int32_t *h_baud,
+                        const int64_t *h_ts_cycles, const uint8_t *h_payload, AfskTxPlan **plan);
+int afsk_tx_plan_destroy(AfskTxPlan *plan);
+/* sample offsets (B+1, host, owned by the plan; each capture starts on a multiple of 8 samples) */
+int afsk_tx_plan_out_offsets(const AfskTxPlan *plan, const int64_t **h_out_off, const int64_t **h_out_len);
+int afsk_tx_synth(AfskTxPlan *plan, const uint8_t *d_payload, int16_t *d_out, void *stream);
+int afsk_tx_synth_host(int device, const uint8_t *h_payload, const int64_t *h_pay_off, int B,
+                       const int32_t *h_baud, const int64_t *h_ts_cycles, int16_t *h_out,
+                       const int64_t *h_out_off);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFSK_B200_H */

@@ -1,0 +1,268 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes), against the committed golden
+outputs of the real reference and against the CPU oracle on seeded inputs.  Bit-exact: every
+quantity on this path is integer/byte work."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_gate_golden, load_rx_golden, load_tx_golden
+
+pytestmark = pytest.mark.gpu
+
+A = pytest.importorskip("afskmodem_b200")
+from afskmodem_b200 import _cabi  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+RX = load_rx_golden()
+TX = load_tx_golden()
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _quiet_and_loaded():
+    A.LOG_LEVEL = 5
+    _cabi.require_device(0)      # no CPU fallback: fail loudly if the GPU/library is missing
+    yield
+    A.LOG_LEVEL = 0
+
+
+def _impair(fr, rng, lead=0, gain=1.0, sigma=0.0, cut=None):
+    x = np.concatenate([np.zeros(lead, np.int16), fr]).astype(np.float64) * gain
+    if sigma > 0:
+        x = x + np.round(rng.normal(0.0, sigma, size=len(x)))
+    x = np.clip(np.trunc(x), -32768, 32767).astype(np.int16)
+    return x if cut is None else x[:cut]
+
+
+def _check_against_oracle(session_batch, caps, bauds, thrs):
+    for i, x in enumerate(caps):
+        o = O.rx_decode(x, int(bauds[i]), int(thrs[i]))
+        got = (int(session_batch.status[i]), int(session_batch.clock[i]), int(session_batch.train_end[i]),
+               int(session_batch.nbits[i]), int(session_batch.nbytes[i]), session_batch.payload(i))
+        want = (o["status"], o["clock"], o["train_end"], o["nbits"], o["nbytes"], o["data"])
+        assert got == want, f"capture {i} baud {bauds[i]} n {len(x)}: {got[:5]} != {want[:5]}"
+
+
+def test_golden_rx_one_mixed_batch():
+    """All golden captures (every baud class, every failure mode) decoded in ONE batch."""
+    metas = [m for m, _ in RX if not m["ctor_exc"]]
+    caps = [x for m, x in RX if not m["ctor_exc"]]
+    samples, offsets = A.modem._concat(caps)
+    s = A.RxSession(offsets, [m["baud"] for m in metas], [m["amp_end"] for m in metas])
+    s.upload(samples)
+    s.run()
+    b = s.download()
+    for i, m in enumerate(metas):
+        name = m["name"]
+        st = int(b.status[i])
+        if m["exc"]:
+            assert st < 0 and list(O.EXC_TEXT[st]) == m["exc"], name
+            continue
+        assert st >= 0, name
+        assert b.payload(i).hex() == m["data_hex"], name
+        assert int(b.clock[i]) == (-1 if m["clock"] is None else m["clock"]), name
+        assert int(b.train_end[i]) == (-1 if m["train_end"] is None else m["train_end"]), name
+        assert int(b.nbits[i]) == (m["nbits"] or 0), name
+        assert int(b.nbytes[i]) == (m["nbytes"] or 0), name
+        assert (st == _cabi.ST_NO_CLOCK) == bool(m["no_clock"]), name
+    s.close()
+
+
+@pytest.mark.parametrize("meta,x", RX, ids=[m["name"] for m, _ in RX])
+def test_golden_rx_load_semantics(meta, x, tmp_path):
+    """Receiver(...).load on a wav: return type / exception rules as the reference."""
+    if meta["ctor_exc"]:
+        with pytest.raises(Exception, match="Invalid baud rate."):
+            A.Receiver(meta["baud"], meta["amp_start"], meta["amp_end"])
+        return
+    r = A.Receiver(meta["baud"], meta["amp_start"], meta["amp_end"])
+    path = str(tmp_path / "c.wav")
+    A.write_wav_frames(path, x)
+    if meta["exc"]:
+        with pytest.raises(Exception) as ei:
+            r.load(path, False)
+        assert [type(ei.value).__name__, str(ei.value)] == meta["exc"]
+        return
+    assert r.load(path, False).hex() == meta["data_hex"]
+    if meta["string_exc"]:
+        with pytest.raises(UnicodeDecodeError):
+            r.load(path, True)
+    else:
+        ret = r.read(path, True)
+        assert type(ret).__name__ == meta["string_ret_type"]
+        if meta["string_ret"] is not None:
+            assert ret == meta["string_ret"]
+
+
+def test_golden_tx():
+    for meta, fr in TX:
+        pl = bytes.fromhex(meta["payload_hex"])
+        if meta["exc"]:
+            with pytest.raises(Exception, match="Invalid baud rate."):
+                A.Transmitter(meta["baud"], meta["training_time"])
+            continue
+        t = A.Transmitter(meta["baud"], meta["training_time"])
+        lens = _cabi.tone_lengths(meta["baud"])
+        if lens[1] != lens[2]:
+            with pytest.raises(NotImplementedError):      # unequal tones: SURVEY §8(f) rank 3, not built yet
+                t.encode_batch([pl])
+            continue
+        mine = t.encode_batch([pl]).frames(0)
+        assert len(mine) == meta["n"], meta["name"]
+        assert hashlib.sha256(mine.astype("<i2").tobytes()).hexdigest() == meta["sha256"], meta["name"]
+        if fr is not None:
+            assert np.array_equal(mine, fr), meta["name"]
+
+
+def test_tx_batch_matches_oracle_mixed():
+    rng = np.random.default_rng(5)
+    bauds = [300, 600, 800, 1200, 2400, 4000, 6000, 12000, 100, 1000, 1500, 2000, 3000]
+    pls = [rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8).tobytes() for _ in bauds]
+    tts = [float(rng.choice([0.5, 0.1, 0.02, 0.0])) for _ in bauds]
+    s = A.TxSession(pls, bauds, [O.ts_cycles(b, t) for b, t in zip(bauds, tts)])
+    s.upload(); s.run()
+    out = s.download()
+    for i, b in enumerate(bauds):
+        assert np.array_equal(out.frames(i), O.tx_frames(pls[i], b, tts[i])), b
+    s.close()
+
+
+@pytest.mark.parametrize("baud", [300, 600, 800, 1200, 2400, 4000, 6000, 12000, 100, 24, 375, 1000])
+def test_random_sweep_vs_oracle(baud):
+    """Seeded impairments per baud: lead silence (arbitrary alignment), gain, AWGN, truncation,
+    thresholds — final bytes AND the four stage integers must equal the oracle's."""
+    rng = np.random.default_rng(baud)
+    caps, thrs = [], []
+    n_cases = 24 if baud >= 300 else 6
+    for k in range(n_cases):
+        pl = rng.integers(0, 256, int(rng.integers(1, 48)), dtype=np.uint8).tobytes()
+        tt = float(rng.choice([0.5, 0.1, 0.05])) if baud >= 300 else 2.0
+        fr = O.tx_frames(pl, baud, tt)
+        x = _impair(fr, rng, lead=int(rng.integers(0, 5000)) if k % 2 else 0,
+                    gain=float(rng.choice([1.0, 0.7, 0.45, 0.3])),
+                    sigma=float(rng.choice([0, 2000, 8000, 14000, 19000, 26000])),
+                    cut=int(rng.integers(2000, len(fr))) if k % 5 == 4 else None)
+        caps.append(x)
+        thrs.append(int(rng.choice([14000, 11000, 8000])))
+    samples, offsets = A.modem._concat(caps)       # arbitrary (unaligned) capture starts
+    s = A.RxSession(offsets, baud, thrs)
+    s.upload(samples); s.run()
+    b = s.download()
+    _check_against_oracle(b, caps, [baud] * len(caps), thrs)
+    # stage-level: raw coded bits of one capture equal the oracle's
+    o = O.rx_decode(caps[0], baud, thrs[0], want_bits=True)
+    if o["status"] == 0:
+        bits, _ = s.planes(0)
+        k0 = (o["train_end"] - o["clock"]) // (48000 // baud)
+        assert np.array_equal(bits[k0:k0 + o["nbits"]].astype(np.uint8), o["bits"])
+    s.close()
+
+
+def test_every_alignment_and_clock_offset():
+    """Capture start alignment (mod 8 samples) x clock offset (lead silence) — exercises every
+    (e0) weight table and the misaligned TMA copies."""
+    rng = np.random.default_rng(3)
+    fr = O.tx_frames(b"alignment!", 1200, 0.1)
+    caps = []
+    for lead in range(0, 48):
+        caps.append(_impair(fr, rng, lead=lead, sigma=3000))
+        caps.append(np.zeros(int(rng.integers(1, 8)), np.int16))      # shifts the next capture's alignment
+    samples, offsets = A.modem._concat(caps)
+    s = A.RxSession(offsets, 1200, 14000)
+    s.upload(samples); s.run()
+    _check_against_oracle(s.download(), caps, [1200] * len(caps), [14000] * len(caps))
+    s.close()
+
+
+def test_threshold_edge_samples():
+    """Samples sitting exactly on the hard-limiter edges (+-512, +-513) and at full scale."""
+    rng = np.random.default_rng(11)
+    vals = np.array([-32768, -32767, -514, -513, -512, -511, -1, 0, 1, 511, 512, 513, 514, 32766, 32767], np.int16)
+    caps = [rng.choice(vals, size=int(n)).astype(np.int16) for n in (4096, 5000, 9999, 20000)]
+    fr = O.tx_frames(b"edge", 1200, 0.1).astype(np.int32)
+    caps.append(np.where(fr > 0, 513, -513).astype(np.int16))
+    caps.append(np.where(fr > 0, 512, -512).astype(np.int16))
+    for thr in (14000, 400, 0, 1, 70000, -5):
+        b = A.Receiver(1200, 18000, thr).decode_batch(caps)
+        _check_against_oracle(b, caps, [1200] * len(caps), [thr] * len(caps))
+
+
+def test_empty_and_ragged_batches():
+    assert len(A.Receiver(1200).decode_batch([])) == 0
+    caps = [np.zeros(0, np.int16), np.zeros(1, np.int16), np.zeros(4095, np.int16), np.zeros(4096, np.int16),
+            O.tx_frames(b"", 1200, 0.5), O.tx_frames(b"x" * 300, 1200, 0.02)]
+    b = A.Receiver(1200).decode_batch(caps)
+    _check_against_oracle(b, caps, [1200] * len(caps), [14000] * len(caps))
+
+
+def test_listen_gate_golden():
+    hello = dict((m["name"], x) for m, x in RX)["readme_hello_1200"]
+    for g in load_gate_golden():
+        s = np.concatenate([np.zeros(g["lead"], np.int16), (hello.astype(np.float64) * g["gain"]).astype(np.int16),
+                            np.zeros(g["tail_zeros"], np.int16)])
+        r = A.Receiver(1200, g["amp_start"], g["amp_end"])
+        rec, a, b = r.listen_gate(s, g["timeout"])[0]
+        assert (rec, a, b) == O.listen_gate(s, g["amp_start"], g["amp_end"], int(g["timeout"] * 48000)), g["name"]
+        if g["exc"]:
+            assert not rec
+            continue
+        assert rec == (not g["timed_out"]), g["name"]
+        got = r.receive_recording(s, g["timeout"], False)
+        assert got.hex() == g["ret_hex"], g["name"]
+        if rec:
+            assert b // 2048 == g["reads"]
+
+
+def test_full_size_roundtrip_property():
+    """BASELINE config #2 shape (1200 baud, 1 KB payloads, 602,400 samples each) at B=256:
+    GPU synth -> AWGN (sigma=8000) -> GPU decode returns every payload; the clean batch returns
+    clock 0 / 14,336 bits everywhere (size-independent round-trip property)."""
+    rng = np.random.default_rng(2)
+    B = 256
+    pls = [rng.integers(0, 256, 1024, dtype=np.uint8).tobytes() for _ in range(B)]
+    tx = A.Transmitter(1200).encode_batch(pls)
+    assert int(tx.out_len[0]) == 602400
+    rx = A.Receiver(1200)
+    s = A.RxSession(tx.out_off, 1200, 14000)
+    s.upload(tx.samples); s.run()
+    b = s.download()
+    assert (b.status == 0).all() and (b.clock == 0).all() and (b.nbits == 14336).all()
+    assert b.payloads() == pls
+    noisy = np.clip(tx.samples.astype(np.int32) + np.round(rng.normal(0, 8000, len(tx.samples))).astype(np.int32),
+                    -32768, 32767).astype(np.int16)
+    s.upload(noisy); s.run()
+    b = s.download()
+    assert b.payloads() == pls and (b.nbits == 14336).all()
+    # spot-check the noisy decode of a few captures against the oracle, stage integers included
+    for i in (0, 100, 255):
+        x = noisy[int(tx.out_off[i]):int(tx.out_off[i]) + 602400]
+        o = O.rx_decode(x, 1200, 14000)
+        assert (int(b.clock[i]), int(b.train_end[i]), int(b.nbits[i]), b.payload(i)) == \
+               (o["clock"], o["train_end"], o["nbits"], o["data"])
+    s.close()
+    del rx
+
+
+def test_long_capture_300_baud():
+    """BASELINE config #4 shape, shortened: 300 baud (160 samples/bit, 4 threads per window), 8 KB payload."""
+    rng = np.random.default_rng(4)
+    pl = rng.integers(0, 256, 8192, dtype=np.uint8).tobytes()
+    fr = A.Transmitter(300).encode_batch([pl]).frames(0)
+    assert np.array_equal(fr, O.tx_frames(pl, 300))
+    x = _impair(fr, rng, lead=1234, sigma=8000)
+    b = A.Receiver(300).decode_batch([x, fr])
+    _check_against_oracle(b, [x, fr], [300, 300], [14000, 14000])
+    assert b.payload(1) == pl
+
+
+def test_abi_rejects_bad_arguments():
+    L = _cabi.lib()
+    assert L.afsk_rx_decode(None, None, None, None, None) == _cabi.AFSK_E_ARG
+    off = np.array([0, 10], dtype=np.int64)
+    s = A.RxSession(off, 1200, 14000)
+    d = _cabi.DeviceBuffer(0, 64)
+    import ctypes as C
+    rc = L.afsk_rx_decode(s.plan, C.c_void_p(d.ptr + 2), C.c_void_p(s.d_out.ptr), C.c_void_p(s.d_res.ptr), None)
+    assert rc == _cabi.AFSK_E_ARG and b"aligned" in L.afsk_last_error()
+    s.close(); d.close()

@@ -23,7 +23,7 @@ SYMBOLS = [
     "afsk_free", "afsk_host_alloc", "afsk_host_free", "afsk_memcpy_h2d", "afsk_memcpy_d2h",
     "afsk_memset", "afsk_stream_create", "afsk_stream_destroy", "afsk_stream_sync",
     "afsk_tone_lengths", "afsk_rx_plan_create", "afsk_rx_plan_destroy", "afsk_rx_plan_out_offsets",
-    "afsk_rx_plan_launches", "afsk_rx_decode", "afsk_rx_plan_planes", "afsk_rx_decode_host",
+    "afsk_rx_plan_launches", "afsk_rx_plan_set_timing", "afsk_rx_plan_demod_time", "afsk_rx_decode", "afsk_rx_plan_planes", "afsk_rx_decode_host",
     "afsk_rx_out_capacity", "afsk_rx_gate", "afsk_tx_num_samples", "afsk_tx_plan_create",
     "afsk_tx_plan_destroy", "afsk_tx_plan_out_offsets", "afsk_tx_synth", "afsk_tx_synth_host",
 ]
@@ -77,8 +77,10 @@ def lib():
     L.afsk_rx_plan_destroy.argtypes = [vp]
     L.afsk_rx_plan_out_offsets.argtypes = [vp, C.POINTER(i64p)]
     L.afsk_rx_plan_launches.argtypes = [vp, C.POINTER(C.c_int)]
+    L.afsk_rx_plan_set_timing.argtypes = [vp, C.c_int]
+    L.afsk_rx_plan_demod_time.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.afsk_rx_decode.argtypes = [vp, vp, vp, vp, vp]
-    L.afsk_rx_plan_planes.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), i64p]
+    L.afsk_rx_plan_planes.argtypes = [vp, C.c_int, C.POINTER(vp), i64p]
     L.afsk_rx_decode_host.argtypes = [C.c_int, i16p, i64p, C.c_int, i32p, i32p, u8p, i64p, C.POINTER(RxResult)]
     L.afsk_rx_out_capacity.argtypes = [C.c_int64, C.c_int]
     L.afsk_rx_out_capacity.restype = C.c_int64

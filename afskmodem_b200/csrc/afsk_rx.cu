@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <map>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "afsk_common.cuh"
@@ -59,8 +60,7 @@ struct DemodParams {
     const int32_t *clock;
     const int32_t *gcaps;        // capture ids of this group, ascending
     const int32_t *gtile_first;  // [ng + 1] prefix of tile counts over gcaps
-    uint32_t *bits;
-    uint32_t *quiet;
+    uint2 *planes;               // {bit word, quiet word} per 32 windows
     int ng;
     int total_items;
     int bf;
@@ -164,38 +164,52 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
 }
 
 // ------------------------------------------------------------------------------ k_demod ----
-// One 32-bit word = two int16 samples.  Returns through the three accumulators:
-//   accM/accS += sum_j T[j] * v_j   with v = +4097 (x > 512), -1 (x < -512), 0 otherwise
-//   accA      += sum_j in-window |x_j|
-// wt packs the +/-1/0 template weights: bytes {mark_lo, mark_hi, space_lo, space_hi}.
-template <bool kAmpHi>
-__device__ __forceinline__ void accum_word(uint32_t w, uint32_t wt, uint32_t aw, int &accM, int &accS,
-                                           unsigned &accA)
+// Per-sample classification (Receiver.__amplify :287-296) and the two getDiff sums (:346-347)
+// in packed integer form.  For a sample x let p = [x > 512], n = [x < -512], c = p - n.
+// With T the +/-1 template (mark: + - + - per quarter, space: + + - -):
+//     sum_j |T[j] - amp[j]| = (65535 * (bf - T.c) + T.(p+n)) / 2          
+// so each window needs U = T.c and Xn = T.n for both templates plus A = sum |x|.
+//
+// Four samples (two 32-bit words) per step:
+//   g  = min((x + 512) mod 2^16, 1025)   VIADDMNMX.U16x2    g == 1025  <=>  |x| > 512
+//   t  = g + 0x7BFF                      bit 15 of each half <=> |x| > 512
+//   S4 / NZ4 = sign / non-zero byte masks of the 4 samples (PRMT with sign replication)
+//   v4 = NZ4 & (S4 | 1)                  bytes: 1 (x > 512), 255 (x < -512), 0
+//   acc += dp4a.u32.s32(v4, T4)          = 256 * T.n + T.c   (IDP.4A; decoded per <= 120 samples)
+//   A   += dp2a.s16.s8(x, (S4 | 1) & inwindow)  = sum sign(x) * x      (IDP.2A)
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
 {
-    const uint32_t m = prmt(w, 0u, 0xBB99u);          // per-half sign mask (0xFFFF where x < 0)
-    const uint32_t a = w ^ m;                         // ones'-complement magnitude
-    const uint32_t ap = a + (m & 0x00010001u);        // |x| as u16 (32768 for -32768), no carry across halves
-    const uint32_t t = ap + 0x7DFF7DFFu;              // bit 15 of each half <=> |x| >= 513  (__amplify :290-292)
-    const uint32_t nzm = prmt(t, 0u, 0xBB99u);        // 0xFFFF where |x| > 512
-    const uint32_t v = nzm & (m | 0x10011001u);       // +4097 / -1 / 0
-    accM = __dp2a_lo((int)v, (int)wt, accM);
-    accS = __dp2a_hi((int)v, (int)wt, accS);
-    accA = kAmpHi ? __dp2a_hi(ap, aw, accA) : __dp2a_lo(ap, aw, accA);
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
-// mark_diff < space_diff (afskmodem.py:346-351) from the packed correlations.
-__device__ __forceinline__ bool decide_bit(int accM, int accS, int bf)
+__device__ __forceinline__ void accum4(uint32_t w0, uint32_t w1, uint32_t mw, uint32_t sw, uint32_t aw, uint32_t k512,
+                                       int &accM, int &accS, int &accA)
 {
-    // acc = 4096*X + U,  X = T.p, U = T.(p-n), |U| <= bf <= 2047
-    const int Um = (int)((unsigned)accM << 20) >> 20, Xm = (accM - Um) >> 12, Wm = 2 * Xm - Um;   // W = T.(p+n)
-    const int Us = (int)((unsigned)accS << 20) >> 20, Xs = (accS - Us) >> 12, Ws = 2 * Xs - Us;
-    // sum_j |T[j] - amp[j]| = (65535*(bf - U) + W) / 2   (always even)
-    const int M = (65535 * (bf - Um) + Wm) >> 1;
-    const int S = (65535 * (bf - Us) + Ws) >> 1;
-    if (S <= M) return false;
-    if (S - M >= bf) return true;
-    return M < (S / bf) * bf;                          // floor(M/bf) < floor(S/bf)
+    const uint32_t g0 = __viaddmin_u16x2(w0, k512, 0x04010401u);
+    const uint32_t g1 = __viaddmin_u16x2(w1, k512, 0x04010401u);
+    const uint32_t t0 = g0 + 0x7BFF7BFFu;
+    const uint32_t t1 = g1 + 0x7BFF7BFFu;
+    const uint32_t s4 = prmt(w0, w1, 0xFDB9u);            // 0xFF where x < 0
+    const uint32_t nz4 = prmt(t0, t1, 0xFDB9u);           // 0xFF where |x| > 512
+    const uint32_t v4 = nz4 & (s4 | 0x01010101u);
+    const uint32_t sg4 = (s4 | 0x01010101u) & aw;         // +1 / -1 inside the window, 0 outside
+    accM = dp4a_us(v4, mw, accM);
+    accS = dp4a_us(v4, sw, accS);
+    accA = __dp2a_lo((int)w0, (int)sg4, accA);
+    accA = __dp2a_hi((int)w1, (int)sg4, accA);
 }
+
+// acc = 256 * Xn + U with |U| <= 127
+__device__ __forceinline__ void unpack_acc(int acc, int &U, int &Xn)
+{
+    const int u = (int)((unsigned)acc << 24) >> 24;
+    U += u;
+    Xn += (acc - u) >> 8;
+}
+
+constexpr int kFlushVecs = 15;      // 120 samples: keeps |T.c| <= 127 inside one packed accumulator
 
 __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
 {
@@ -211,31 +225,28 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     uint64_t *empty = full + kMaxStages;
     uint8_t *resbuf = reinterpret_cast<uint8_t *>(empty + kMaxStages);   // [2][kConsumerThreads]
 
-    // ---- template weight table: entry (part, e, i) covers samples r = 8i + 2j + h - e of the
-    //      thread segment; window position p = part*seg + r; quarter p/q selects the template sign.
+    // ---- template weight table: entry (part, e, i) covers samples r = 8i + s - e (s = 0..7) of
+    //      the thread segment; window position pos = part*seg + r; quarter pos/q gives the sign.
+    //      Layout per entry: {mark[0..3], mark[4..7], space[0..3], space[4..7]} {inwin[0..3], inwin[4..7], 0, 0}
     {
         const int q = p.bf >> 2;
         for (int idx = tid; idx < wtab_entries; idx += kDemodThreads) {
             const int i = idx % p.nv, e = (idx / p.nv) & 7, part = idx / (p.nv * 8);
             const int seg_lo = part * p.seg, seg_hi = min(p.bf, seg_lo + p.seg);
-            uint32_t ms[4], amp[2] = {0u, 0u};
+            uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u}, in[2] = {0u, 0u};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                ms[j] = 0;
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int r = 8 * i + 2 * j + hh - e, pos = seg_lo + r;
-                    if (r >= 0 && pos < seg_hi) {
-                        const int qd = pos / q;
-                        const uint32_t mk = (qd & 1) ? 0xFFu : 0x01u;   // mark : + - + -
-                        const uint32_t sp = (qd & 2) ? 0xFFu : 0x01u;   // space: + + - -
-                        ms[j] |= (mk << (8 * hh)) | (sp << (16 + 8 * hh));
-                        amp[j >> 1] |= 1u << (8 * (2 * (j & 1) + hh));
-                    }
+            for (int s = 0; s < 8; s++) {
+                const int r = 8 * i + s - e, pos = seg_lo + r;
+                if (r >= 0 && pos < seg_hi) {
+                    const int qd = pos / q;
+                    const int sh = 8 * (s & 3);
+                    mk[s >> 2] |= ((qd & 1) ? 0xFFu : 0x01u) << sh;    // mark : + - + -
+                    sp[s >> 2] |= ((qd & 2) ? 0xFFu : 0x01u) << sh;    // space: + + - -
+                    in[s >> 2] |= 0xFFu << sh;
                 }
             }
-            wtab[2 * idx] = make_uint4(ms[0], ms[1], ms[2], ms[3]);
-            wtab[2 * idx + 1] = make_uint4(amp[0], amp[1], 0u, 0u);
+            wtab[2 * idx] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
+            wtab[2 * idx + 1] = make_uint4(in[0], in[1], 0u, 0u);
         }
     }
     if (tid == 0) {
@@ -265,6 +276,8 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
         CapDesc d;
         long long K = 0;
         int clk = 0;
+        int s = 0;
+        uint32_t ph = 0;                                       // parity of the use count of stage s
         for (int it = lo; it < hi; ++it) {
             while (it >= next_first) {
                 ci++;
@@ -284,8 +297,9 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
             const int nwin = nw <= 0 ? 0 : (nw > p.wt ? p.wt : (int)nw);
             const long long g0 = d.off + clk + k0t * p.bf;          // first sample of the tile
             const long long ga = g0 & ~7LL;
-            const int n = it - lo, s = n % S;
-            if (n >= S) mbar_wait(&empty[s], ((n / S) & 1) ^ 1);
+            if (it - lo >= S) {
+                while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(64);
+            }
             TileMeta m;
             m.e0 = (int)(g0 - ga);
             m.nwin = nwin;
@@ -301,6 +315,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
             } else {
                 mbar_arrive(&full[s]);
             }
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
         return;
     }
@@ -309,35 +324,51 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     const int w = tid >> p.tpw_log2, part = tid & (tpw - 1);
     const int bf = p.bf, nv = p.nv;
     const int rel0 = w * bf + part * p.seg;
+    const int two_bf = 2 * bf;
+    // VIADDMNMX takes one immediate; derive the other constant from a runtime value so that it
+    // lives in one register instead of being re-materialised before every use (stages < 65536)
+    const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
+    int s = 0;
+    uint32_t ph = 0;
     for (int n = 0; n < hi - lo; ++n) {
-        const int s = n % S;
-        mbar_wait(&full[s], (n / S) & 1);
+        mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
         bool bit = false, quiet = false;
         if (m.nwin > 0) {
             const int rel = m.e0 + rel0;
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (rel >> 3);
             const uint4 *wp = wtab + 2 * ((part * 8 + (rel & 7)) * nv);
-            int accM = 0, accS = 0;
-            unsigned accA = 0;
-#pragma unroll 2
-            for (int i = 0; i < nv; i++) {
-                const uint4 dv = dp[i];
-                const uint4 wv = wp[2 * i];
-                const uint2 av = *reinterpret_cast<const uint2 *>(wp + 2 * i + 1);
-                accum_word<false>(dv.x, wv.x, av.x, accM, accS, accA);
-                accum_word<true>(dv.y, wv.y, av.x, accM, accS, accA);
-                accum_word<false>(dv.z, wv.z, av.y, accM, accS, accA);
-                accum_word<true>(dv.w, wv.w, av.y, accM, accS, accA);
+            int Um = 0, Nm = 0, Us = 0, Ns = 0, accA = 0;
+            for (int i0 = 0; i0 < nv; i0 += kFlushVecs) {
+                const int i1 = min(nv, i0 + kFlushVecs);
+                int accM = 0, accS = 0;
+#pragma unroll 3
+                for (int i = i0; i < i1; i++) {
+                    const uint4 dv = dp[i];
+                    const uint4 wv = wp[2 * i];
+                    const uint2 av = *reinterpret_cast<const uint2 *>(wp + 2 * i + 1);
+                    accum4(dv.x, dv.y, wv.x, wv.z, av.x, k512, accM, accS, accA);
+                    accum4(dv.z, dv.w, wv.y, wv.w, av.y, k512, accM, accS, accA);
+                }
+                unpack_acc(accM, Um, Nm);
+                unpack_acc(accS, Us, Ns);
             }
             for (int o = 1; o < tpw; o <<= 1) {
-                accM += __shfl_xor_sync(0xFFFFFFFFu, accM, o);
-                accS += __shfl_xor_sync(0xFFFFFFFFu, accS, o);
+                Um += __shfl_xor_sync(0xFFFFFFFFu, Um, o);
+                Nm += __shfl_xor_sync(0xFFFFFFFFu, Nm, o);
+                Us += __shfl_xor_sync(0xFFFFFFFFu, Us, o);
+                Ns += __shfl_xor_sync(0xFFFFFFFFu, Ns, o);
                 accA += __shfl_xor_sync(0xFFFFFFFFu, accA, o);
             }
+            // 2 * sum|T - amp| = 65535 * (bf - U) + (U + 2 * Xn)      (mark_diff < space_diff :346-351)
+            const int M2 = 65535 * (bf - Um) + Um + 2 * Nm;
+            const int S2 = 65535 * (bf - Us) + Us + 2 * Ns;
+            const int dlt = S2 - M2;
+            bool b1 = dlt >= two_bf;
+            if (dlt > 0 && dlt < two_bf) b1 = M2 < (S2 / two_bf) * two_bf;   // floor(M/bf) < floor(S/bf)
             const bool valid = (part == 0) && (w < m.nwin);
-            bit = valid && decide_bit(accM, accS, bf);
-            quiet = valid && ((int)accA < m.thr_bf);            // getAmplitude(chunk) < amp_end :375
+            bit = valid && b1;
+            quiet = valid && (accA < m.thr_bf);                // getAmplitude(chunk) < amp_end :375
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);                   // stage may be refilled
@@ -345,10 +376,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
             if (p.tpw_log2 == 0) {
                 const uint32_t bw = __ballot_sync(0xFFFFFFFFu, bit);
                 const uint32_t qw = __ballot_sync(0xFFFFFFFFu, quiet);
-                if (lane == 0 && warp * 32 < m.nwin) {
-                    p.bits[m.word_base + warp] = bw;
-                    p.quiet[m.word_base + warp] = qw;
-                }
+                if (lane == 0 && warp * 32 < m.nwin) p.planes[m.word_base + warp] = make_uint2(bw, qw);
             } else {
                 uint8_t *rb = resbuf + (n & 1) * kConsumerThreads;
                 if (part == 0) rb[w] = (uint8_t)((bit ? 1 : 0) | (quiet ? 2 : 0));
@@ -357,13 +385,11 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
                     const uint8_t r = rb[warp * 32 + lane];
                     const uint32_t bw = __ballot_sync(0xFFFFFFFFu, r & 1);
                     const uint32_t qw = __ballot_sync(0xFFFFFFFFu, r & 2);
-                    if (lane == 0 && warp * 32 < m.nwin) {
-                        p.bits[m.word_base + warp] = bw;
-                        p.quiet[m.word_base + warp] = qw;
-                    }
+                    if (lane == 0 && warp * 32 < m.nwin) p.planes[m.word_base + warp] = make_uint2(bw, qw);
                 }
             }
         }
+        if (++s == S) { s = 0; ph ^= 1u; }
     }
 }
 
@@ -394,8 +420,7 @@ __device__ __forceinline__ uint32_t hamming74_nibble(uint32_t cw)
 
 __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restrict__ caps,
                                                          const int32_t *__restrict__ clock,
-                                                         const uint32_t *__restrict__ bits,
-                                                         const uint32_t *__restrict__ quiet,
+                                                         const uint2 *__restrict__ planes,
                                                          uint8_t *__restrict__ out,
                                                          AfskRxResult *__restrict__ res)
 {
@@ -406,8 +431,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
     const int clk = clock[c];
     const long long K = num_windows(d.n, d.bf, clk);
     const long long nwords = (K + 31) >> 5;
-    const uint32_t *B = bits + d.plane_base;
-    const uint32_t *Q = quiet + d.plane_base;
+    const uint2 *PL = planes + d.plane_base;
     const long long NONE = 0x7FFFFFFFFFFFFFFFLL;
 
     // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
@@ -416,7 +440,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
         const long long j = base + tid;
         long long cand = NONE;
         if (j < nwords) {
-            const uint64_t v = ((uint64_t)B[j] << 32) | (j ? B[j - 1] : 0u);
+            const uint64_t v = ((uint64_t)PL[j].x << 32) | (j ? PL[j - 1].x : 0u);
             uint32_t M = (uint32_t)((v >> 29) & ~(v >> 30) & ~(v >> 31) & ~(v >> 32));
             const long long rem = K - 32 * j;
             if (rem < 32) M &= (1u << rem) - 1u;
@@ -432,7 +456,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
         const long long j = base + tid;
         long long cand = NONE;
         if (j < nwords) {
-            uint32_t M = Q[j];
+            uint32_t M = PL[j].y;
             if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
             const long long rem = K - 32 * j;
             if (rem < 32) M &= (1u << rem) - 1u;
@@ -447,7 +471,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
     uint8_t *o = out + d.out_off;
     for (long long i = tid; i < nbytes; i += kFrameThreads) {
         const long long pos = k0 + 14 * i;
-        const uint32_t lo = B[pos >> 5], hi = B[(pos >> 5) + 1];
+        const uint32_t lo = PL[pos >> 5].x, hi = PL[(pos >> 5) + 1].x;
         const uint32_t val = __funnelshift_r(lo, hi, (uint32_t)(pos & 31));
         o[i] = (uint8_t)((hamming74_nibble(val & 0x7Fu) << 4) | hamming74_nibble((val >> 7) & 0x7Fu));
     }
@@ -546,8 +570,10 @@ struct AfskRxPlan {
     std::vector<Group> groups;
     CapDesc *d_caps = nullptr;
     int32_t *d_clock = nullptr;
-    uint32_t *d_bits = nullptr, *d_quiet = nullptr;
+    uint2 *d_planes = nullptr;
     int64_t plane_words = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
 
 static size_t demod_smem_bytes(const Group &g)
@@ -655,8 +681,7 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
     };
     up((void **)&P->d_caps, P->caps.data(), sizeof(CapDesc) * B);
     if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_clock, sizeof(int32_t) * (B ? B : 1));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_bits, sizeof(uint32_t) * P->plane_words);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_quiet, sizeof(uint32_t) * P->plane_words);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_planes, sizeof(uint2) * P->plane_words);
     for (Group &g : P->groups) {
         up((void **)&g.d_caps, g.caps.data(), sizeof(int32_t) * g.caps.size());
         up((void **)&g.d_tile_first, g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());
@@ -679,7 +704,8 @@ int afsk_rx_plan_destroy(AfskRxPlan *P)
 {
     if (!P) return AFSK_OK;
     AfskDeviceGuard guard(P->device);
-    cudaFree(P->d_caps); cudaFree(P->d_clock); cudaFree(P->d_bits); cudaFree(P->d_quiet);
+    for (auto &ev : P->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    cudaFree(P->d_caps); cudaFree(P->d_clock); cudaFree(P->d_planes);
     for (Group &g : P->groups) { cudaFree(g.d_caps); cudaFree(g.d_tile_first); }
     delete P;
     return AFSK_OK;
@@ -699,13 +725,39 @@ int afsk_rx_plan_launches(const AfskRxPlan *P, int *launches)
     return AFSK_OK;
 }
 
-int afsk_rx_plan_planes(const AfskRxPlan *P, int capture, const uint32_t **d_bits, const uint32_t **d_quiet,
-                        int64_t *max_windows)
+int afsk_rx_plan_set_timing(AfskRxPlan *P, int enable)
+{
+    if (!P) return AFSK_E_ARG;
+    P->timing = enable != 0;
+    return AFSK_OK;
+}
+
+int afsk_rx_plan_demod_time(AfskRxPlan *P, float *ms_total, int *launches)
+{
+    if (!P || !ms_total || !launches) return AFSK_E_ARG;
+    AfskDeviceGuard guard(P->device);
+    float total = 0.f;
+    int n = 0;
+    for (auto &ev : P->timing_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+            total += ms;
+            n++;
+        }
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    P->timing_events.clear();
+    *ms_total = total;
+    *launches = n;
+    return AFSK_OK;
+}
+
+int afsk_rx_plan_planes(const AfskRxPlan *P, int capture, const uint32_t **d_planes, int64_t *max_windows)
 {
     if (!P || capture < 0 || capture >= P->B) return AFSK_E_ARG;
     const CapDesc &d = P->caps[capture];
-    if (d_bits) *d_bits = P->d_bits + d.plane_base;
-    if (d_quiet) *d_quiet = P->d_quiet + d.plane_base;
+    if (d_planes) *d_planes = reinterpret_cast<const uint32_t *>(P->d_planes + d.plane_base);
     if (max_windows) *max_windows = d.status0 == 0 ? (d.n - d.bf + d.bf - 1) / d.bf : 0;
     return AFSK_OK;
 }
@@ -723,13 +775,20 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         DemodParams p;
         p.samples = d_samples; p.caps = P->d_caps; p.clock = P->d_clock;
         p.gcaps = g.d_caps; p.gtile_first = g.d_tile_first;
-        p.bits = P->d_bits; p.quiet = P->d_quiet;
+        p.planes = P->d_planes;
         p.ng = (int)g.caps.size(); p.total_items = g.tile_first.back();
         p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.wt = g.wt;
         p.stage_bytes = g.stage_bytes; p.stages = g.stages;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+            cudaEventRecord(e0, st);
         k_demod<<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        if (e0 && e1) {
+            cudaEventRecord(e1, st);
+            P->timing_events.emplace_back(e0, e1);
+        }
     }
-    k_frame<<<P->B, kFrameThreads, 0, st>>>(P->d_caps, P->d_clock, P->d_bits, P->d_quiet, d_out, d_res);
+    k_frame<<<P->B, kFrameThreads, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     AFSK_CUDA(cudaGetLastError());
     return AFSK_OK;
 }

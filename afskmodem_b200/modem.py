@@ -221,6 +221,15 @@ class RxSession:
         _cabi.check(_cabi.lib().afsk_rx_decode(self.plan, C.c_void_p(p), C.c_void_p(self.d_out.ptr),
                                                C.c_void_p(self.d_res.ptr), C.c_void_p(stream or 0)))
 
+    def set_timing(self, enable: bool):
+        _cabi.check(_cabi.lib().afsk_rx_plan_set_timing(self.plan, 1 if enable else 0))
+
+    def demod_time(self):
+        """(summed k_demod milliseconds, launches) since the last query; synchronizes."""
+        ms, n = C.c_float(0), C.c_int(0)
+        _cabi.check(_cabi.lib().afsk_rx_plan_demod_time(self.plan, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def download(self, stream=None, res_host: np.ndarray | None = None, blob_host: np.ndarray | None = None) -> RxBatch:
         res = res_host if res_host is not None else np.zeros(self.B, dtype=_cabi.RX_RESULT_DTYPE)
         blob = blob_host if blob_host is not None else np.zeros(int(self.out_off[-1]), dtype=np.uint8)
@@ -233,17 +242,16 @@ class RxSession:
     def planes(self, capture: int):
         """(bits, quiet) numpy bool arrays of capture's windows after a run — stage-level parity."""
         L = _cabi.lib()
-        pb, pq, mw = C.c_void_p(), C.c_void_p(), C.c_int64(0)
-        _cabi.check(L.afsk_rx_plan_planes(self.plan, capture, C.byref(pb), C.byref(pq), C.byref(mw)))
+        pp, mw = C.c_void_p(), C.c_int64(0)
+        _cabi.check(L.afsk_rx_plan_planes(self.plan, capture, C.byref(pp), C.byref(mw)))
         nw = (mw.value + 31) // 32
-        out = []
-        for p in (pb, pq):
-            words = np.zeros(max(nw, 1), dtype=np.uint32)
-            if nw:
-                _cabi.check(L.afsk_memcpy_d2h(self.device, C.c_void_p(words.ctypes.data), p, nw * 4, None))
-            _cabi.stream_sync(self.device)
-            out.append(np.unpackbits(words.view(np.uint8), bitorder="little")[:mw.value].astype(bool))
-        return out[0], out[1]
+        words = np.zeros((max(nw, 1), 2), dtype=np.uint32)
+        if nw:
+            _cabi.check(L.afsk_memcpy_d2h(self.device, C.c_void_p(words.ctypes.data), pp, nw * 8, None))
+        _cabi.stream_sync(self.device)
+        unpack = lambda col: np.unpackbits(np.ascontiguousarray(words[:, col]).view(np.uint8),  # noqa: E731
+                                           bitorder="little")[:mw.value].astype(bool)
+        return unpack(0), unpack(1)
 
 
 def _concat(captures):

@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — batched AFSK decode throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 4096 independent 1200-baud captures per GPU, 1 KB random
+payload each, synthesized by the GPU transmitter, 25 % with U[0,4000) frames of lead silence,
+AWGN sigma drawn per capture from {0,2k,8k,14k,19k,26k} (weights 1,2,3,2,1,1), all over the whole
+capture.  ~2.47 G samples = 4.9 GB of int16 per GPU: larger than L2, so no flush
+is needed between timed iterations.  A step = one decode of the whole batch.
+
+  value        decoded Msamples/s, inputs resident in HBM, CUDA events, max over ranks
+  e2e          same metric through Receiver.decode_batch with HOST (pinned) buffers: plan,
+               H2D of all samples, kernels, D2H of results + payloads inside the timed region
+  roofline     k_demod: 2 bytes/sample x samples per launch / its CUDA-event duration vs the
+               measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline the C oracle port of the reference algorithm on the host cores (rank 0, N=1)
+
+--impl reference times that same oracle port (the reference is pure Python and cannot travel
+to the GPU box) on a bounded sample of the workload, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BAUD = 1200
+PAYLOAD = 1024
+AMP_END = 14000
+SIGMAS = np.array([0, 2000, 8000, 14000, 19000, 26000], dtype=np.float64)
+SIGMA_W = np.array([1, 2, 3, 2, 1, 1], dtype=np.float64) / 10.0
+CLEAN_N = 602400                 # frames Transmitter(1200).save writes for 1 KB
+
+
+def workload_name(B):
+    return f"c2: {B} x 1200-baud captures, 1 KB payload, AWGN mix, 25% lead silence"
+
+
+def capture_recipe(B, rank):
+    rng = np.random.default_rng([2, rank])
+    payloads = rng.integers(0, 256, size=(B, PAYLOAD), dtype=np.uint8)
+    lead = np.where(rng.random(B) < 0.25, rng.integers(0, 4000, B), 0).astype(np.int64)
+    sigma = rng.choice(SIGMAS, size=B, p=SIGMA_W)
+    return payloads, lead, sigma
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_batch_on_gpu(B, rank, device):
+    """Synthesizes the batch with the GPU transmitter, then lead silence + AWGN with torch (plumbing)."""
+    import torch
+
+    import afskmodem_b200 as A
+    payloads, lead, sigma = capture_recipe(B, rank)
+    ts = int(BAUD * 0.5 / 2)
+    import ctypes
+    dev = torch.device("cuda", device)
+    tx = A.TxSession([p.tobytes() for p in payloads], BAUD, ts, device)
+    tx.upload()
+    assert int(tx.out_len[0]) == CLEAN_N
+    # synthesize straight into a torch-owned buffer (caller-owned device pointer through the C ABI)
+    clean = torch.empty(int(tx.out_off[-1]) + 64, dtype=torch.int16, device=dev)
+    A._cabi.check(A._cabi.lib().afsk_tx_synth(tx.plan, ctypes.c_void_p(tx.d_pay.ptr), ctypes.c_void_p(clean.data_ptr()),
+                                              None))
+    A._cabi.stream_sync(device)
+    lens = lead + CLEAN_N
+    offsets = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    total = int(offsets[-1])
+    samples = torch.zeros(total + 64, dtype=torch.int16, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    chunk = 128
+    for c0 in range(0, B, chunk):
+        c1 = min(B, c0 + chunk)
+        for c in range(c0, c1):
+            o = int(offsets[c]) + int(lead[c])
+            samples[o:o + CLEAN_N] = clean[int(tx.out_off[c]):int(tx.out_off[c]) + CLEAN_N]
+        a, b = int(offsets[c0]), int(offsets[c1])
+        sig = torch.repeat_interleave(torch.as_tensor(sigma[c0:c1], dtype=torch.float32, device=dev),
+                                      torch.as_tensor(lens[c0:c1], device=dev))
+        noise = torch.round(torch.randn(b - a, generator=gen, device=dev, dtype=torch.float32) * sig)
+        samples[a:b] = torch.clamp(samples[a:b].to(torch.float32) + noise, -32768, 32767).to(torch.int16)
+        del sig, noise
+    tx.close()
+    del clean
+    torch.cuda.synchronize(dev)
+    return samples, offsets, payloads, sigma, lead
+
+
+def host_sample_batch(B, rank=0):
+    """Same recipe on the host (oracle transmitter + numpy AWGN) for the reference arm."""
+    from oracle import oracle as O
+    payloads, lead, sigma = capture_recipe(B, rank)
+    rng = np.random.default_rng([3, rank])
+    caps = []
+    for c in range(B):
+        fr = O.tx_frames(payloads[c].tobytes(), BAUD, 0.5)
+        x = np.concatenate([np.zeros(int(lead[c]), np.int16), fr]).astype(np.float32)
+        if sigma[c] > 0:
+            x += np.round(rng.normal(0.0, sigma[c], len(x))).astype(np.float32)
+        caps.append(np.clip(x, -32768, 32767).astype(np.int16))
+    lens = np.array([len(c) for c in caps], dtype=np.int64)
+    off = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    return np.concatenate(caps), off, payloads
+
+
+def run_reference(args):
+    """Reference arm: the oracle port of afskmodem.py's Receiver.load compute, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    nsample = 256
+    samples, off, payloads = host_sample_batch(nsample)
+    for _ in range(max(args.warmup, 1)):
+        O.rx_decode_batch(samples, off, BAUD, AMP_END, threads=cores)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for _ in range(args.steps):
+        datas, _ = O.rx_decode_batch(samples, off, BAUD, AMP_END, threads=cores)
+        nbytes += sum(len(d) for d in datas)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1000
+    val = float(off[-1]) / (ms / 1000) / 1e6
+    sample = f"{nsample} captures of the c2 recipe ({int(off[-1])} samples) per step, C port of afskmodem.py on {cores} threads"
+    line = {"impl": "reference", "metric": "decoded Msamples/s", "value": val, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
+            "data": "synthetic", "mbit_s": 8 * nbytes / dt / 1e6,
+            "config": {"workload": workload_name(4096), "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--captures", type=int, default=4096, help="captures per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-captures", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import afskmodem_b200 as A
+    from afskmodem_b200 import _cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    A.LOG_LEVEL = 5
+    _cabi.require_device(local)              # no CPU fallback
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.captures
+
+    samples, offsets, payloads, sigma, lead = build_batch_on_gpu(B, rank, local)
+    total = int(offsets[-1])
+    sess = A.RxSession(offsets, BAUD, AMP_END, local)
+    sess.bind(samples.data_ptr())
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    # ---- correctness spot check against the oracle (outside every timed region) ----
+    sess.run(stream)
+    batch = sess.download(stream)
+    decoded_bytes = batch.total_payload_bytes()
+    parity_checked = 0
+    if rank == 0:
+        from oracle import oracle as O
+        picks = sorted(set([0, 1, 2, 3, B // 2, B - 1] + [int(np.argmax(sigma == s)) for s in SIGMAS if (sigma == s).any()]))
+        for c in picks:
+            x = samples[int(offsets[c]):int(offsets[c + 1])].cpu().numpy()
+            o = O.rx_decode(x, BAUD, AMP_END)
+            got = (int(batch.status[c]), int(batch.clock[c]), int(batch.train_end[c]), int(batch.nbits[c]), batch.payload(c))
+            want = (o["status"], o["clock"], o["train_end"], o["nbits"], o["data"])
+            if got != want:
+                raise SystemExit(f"PARITY FAILURE on capture {c}: {got[:4]} != {want[:4]}")
+            parity_checked += 1
+    exact = int(sum(batch.payload(c) == payloads[c].tobytes() for c in range(B)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (value) ----
+    for _ in range(args.warmup):
+        sess.run(stream)
+    # ramp clocks under the same load for ~1 s with the nvidia-smi sampler running, then time
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t_end = time.time() + float(os.environ.get("AFSK_BENCH_PRELOAD_S", "1.0"))
+    while time.time() < t_end:
+        sess.run(stream)
+        torch.cuda.synchronize(dev)
+    sess.set_timing(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sess.run(stream)
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    demod_ms, demod_launches = sess.demod_time()
+    sess.set_timing(False)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    tot = torch.tensor([float(total), float(decoded_bytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    all_samples, all_bytes = float(tot[0].item()), float(tot[1].item())
+    value = all_samples / (ms_per_step / 1000) / 1e6
+    mbit = 8 * all_bytes / (ms_per_step / 1000) / 1e6
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        pin = _cabi.PinnedArray((total + 64,), np.int16)
+        pin.array[:total] = samples[:total].cpu().numpy()
+        rx = A.Receiver(BAUD, 18000, AMP_END, device=local)
+        rx.decode_batch(pin.array, offsets)            # warm-up (first call pays context / allocator set-up)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.e2e_steps):
+            hb = rx.decode_batch(pin.array, offsets)
+        s1.record()
+        barrier()
+        te = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item()) / args.e2e_steps
+        assert hb.total_payload_bytes() == decoded_bytes
+        e2e = {"value": all_samples / (e2e_ms / 1000) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": total * 2, "d2h_bytes_per_step": int(32 * B + hb.out_off[-1]),
+               "api": "Receiver.decode_batch(pinned int16 samples, offsets)", "steps": args.e2e_steps}
+        pin.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    demod_avg_ms = demod_ms / max(demod_launches, 1)
+    achieved = 2.0 * total / (demod_avg_ms / 1000) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("k_demod_c2_dram_bytes_per_launch")
+    roofline = {"kernel": "k_demod", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 2 * total, "avg_launch_ms": demod_avg_ms,
+                "share_of_step": demod_avg_ms / (elapsed_ms / args.steps)}
+
+    # ---- CPU baseline: oracle port on the host cores, bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        nc = min(B, args.cpu_captures)
+        hs = samples[:int(offsets[nc])].cpu().numpy()
+        O.rx_decode_batch(hs[:int(offsets[min(nc, 64)])], offsets[:min(nc, 64) + 1], BAUD, AMP_END, threads=cores)
+        t0 = time.perf_counter()
+        datas, _ = O.rx_decode_batch(hs, offsets[:nc + 1], BAUD, AMP_END, threads=cores)
+        dt = time.perf_counter() - t0
+        assert datas == [batch.payload(c) for c in range(nc)], "GPU payloads != oracle payloads on the CPU sample"
+        parity_checked = max(parity_checked, nc)
+        cpu = {"value": float(offsets[nc]) / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "sample": f"first {nc} captures of the workload ({int(offsets[nc])} samples), C port of afskmodem.py "
+                         f"Receiver.load compute, {cores} threads, {dt:.2f} s wall; every payload equal to the GPU's"}
+
+    line = {"metric": "decoded Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "mbit_s": mbit,
+            "config": {"workload": workload_name(B), "captures_per_gpu": B, "samples_per_gpu": total,
+                       "baud": BAUD, "payload_bytes": PAYLOAD, "l2_policy": "inputs (4.9 GB/GPU) larger than L2; no flush",
+                       "payloads_exact": exact, "parity_checked_vs_oracle": parity_checked},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * sess.launches,
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    sess.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

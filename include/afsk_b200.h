@@ -106,10 +106,18 @@ int afsk_rx_plan_launches(const AfskRxPlan *plan, int *launches);
  */
 int afsk_rx_decode(AfskRxPlan *plan, const int16_t *d_samples, uint8_t *d_out, AfskRxResult *d_res,
                    void *stream);
-/* raw coded bits / quiet flags of capture c after a decode, packed LSB-first, for diagnostics
- * and stage-level parity tests: window k of capture c is bit (k & 31) of word k >> 5. */
-int afsk_rx_plan_planes(const AfskRxPlan *plan, int capture, const uint32_t **d_bits,
-                        const uint32_t **d_quiet, int64_t *max_windows);
+/*
+ * Optional in-line timing of the dominant kernel (k_demod) for roofline reporting: when enabled,
+ * every afsk_rx_decode brackets each k_demod launch with CUDA events on the caller's stream.
+ * afsk_rx_plan_demod_time synchronizes those events, returns their summed duration and launch
+ * count since the last query, and clears them.
+ */
+int afsk_rx_plan_set_timing(AfskRxPlan *plan, int enable);
+int afsk_rx_plan_demod_time(AfskRxPlan *plan, float *ms_total, int *launches);
+/* raw decision / quiet flags of capture c after a decode, for diagnostics and stage-level parity
+ * tests: d_planes points at interleaved uint32 pairs {bits, quiet}; window k of the capture is
+ * bit (k & 31) of pair k >> 5 (LSB first). */
+int afsk_rx_plan_planes(const AfskRxPlan *plan, int capture, const uint32_t **d_planes, int64_t *max_windows);
 /*
  * Host-buffer convenience (what a drop-in Receiver.load calls): H2D, decode, D2H on `device`.
  * h_out_off[B+1] are capacity offsets into h_out (use afsk_rx_out_capacity per capture).

@@ -67,6 +67,8 @@ struct DemodParams {
     int tpw_log2;     // threads per window = 1 << tpw_log2
     int seg;          // samples per thread segment = ceil(bf / tpw)
     int nv;           // 16-byte vectors each thread reads
+    int nt;           // weight-table entries per (part, alignment): nv, or nv - 1 in merge mode
+    int merge;        // seg % 8 == 0: head and tail partial vectors are merged into one
     int wt;           // windows per tile = kConsumerThreads >> tpw_log2
     int stage_bytes;
     int stages;
@@ -211,6 +213,11 @@ __device__ __forceinline__ void unpack_acc(int acc, int &U, int &Xn)
 
 constexpr int kFlushVecs = 15;      // 120 samples: keeps |T.c| <= 127 inside one packed accumulator
 
+// kNT > 0: the number of vector steps per thread is a compile-time constant (fully unrolled, one
+// packed accumulator); kNT == 0: run-time count with a flush every kFlushVecs vectors.
+// kMerge: the thread segment is a multiple of 8 samples, so the partial head vector (slots >= e)
+// and the partial tail vector (slots < e) are merged into one full vector with 4 PRMTs.
+template <int kNT, bool kMerge>
 __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -219,24 +226,28 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     const int tpw = 1 << p.tpw_log2;
     uint8_t *stage_base = smem;
     uint4 *wtab = reinterpret_cast<uint4 *>(smem + (size_t)S * p.stage_bytes);
-    const int wtab_entries = tpw * 8 * p.nv;                       // 32 bytes each
+    const int wtab_entries = tpw * 8 * p.nt;                       // 32 bytes each
     TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + 2 * wtab_entries);
     uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
     uint64_t *empty = full + kMaxStages;
     uint8_t *resbuf = reinterpret_cast<uint8_t *>(empty + kMaxStages);   // [2][kConsumerThreads]
 
-    // ---- template weight table: entry (part, e, i) covers samples r = 8i + s - e (s = 0..7) of
-    //      the thread segment; window position pos = part*seg + r; quarter pos/q gives the sign.
-    //      Layout per entry: {mark[0..3], mark[4..7], space[0..3], space[4..7]} {inwin[0..3], inwin[4..7], 0, 0}
+    // ---- template weight table: entry (part, e, i), slot s = 0..7 of vector i covers segment
+    //      sample r = 8i + s - e (merge mode, i == 0: slots below e come from the tail vector,
+    //      r = 8*nt + s - e); window position pos = part*seg + r; quarter pos/q gives the sign.
+    //      Layout: {mark[0..3], mark[4..7], space[0..3], space[4..7]} {inwin[0..3], inwin[4..7], selA, selB}
+    //      selA/selB: PRMT selectors (16 bits each) building the merged vector from head/tail words.
     {
         const int q = p.bf >> 2;
         for (int idx = tid; idx < wtab_entries; idx += kDemodThreads) {
-            const int i = idx % p.nv, e = (idx / p.nv) & 7, part = idx / (p.nv * 8);
+            const int i = idx % p.nt, e = (idx / p.nt) & 7, part = idx / (p.nt * 8);
             const int seg_lo = part * p.seg, seg_hi = min(p.bf, seg_lo + p.seg);
-            uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u}, in[2] = {0u, 0u};
+            uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u}, in[2] = {0u, 0u}, sel[2] = {0u, 0u};
 #pragma unroll
             for (int s = 0; s < 8; s++) {
-                const int r = 8 * i + s - e, pos = seg_lo + r;
+                int r = 8 * i + s - e;
+                if (kMerge && i == 0 && s < e) r += 8 * p.nt;
+                const int pos = seg_lo + r;
                 if (r >= 0 && pos < seg_hi) {
                     const int qd = pos / q;
                     const int sh = 8 * (s & 3);
@@ -245,8 +256,13 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
                     in[s >> 2] |= 0xFFu << sh;
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t sj = (2 * j >= e) ? 0x3210u : ((2 * j + 1 < e) ? 0x7654u : 0x3254u);
+                sel[j >> 1] |= sj << (16 * (j & 1));
+            }
             wtab[2 * idx] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
-            wtab[2 * idx + 1] = make_uint4(in[0], in[1], 0u, 0u);
+            wtab[2 * idx + 1] = make_uint4(in[0], in[1], sel[0], sel[1]);
         }
     }
     if (tid == 0) {
@@ -298,7 +314,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
             const long long g0 = d.off + clk + k0t * p.bf;          // first sample of the tile
             const long long ga = g0 & ~7LL;
             if (it - lo >= S) {
-                while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(64);
+                while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(256);
             }
             TileMeta m;
             m.e0 = (int)(g0 - ga);
@@ -337,21 +353,41 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
         if (m.nwin > 0) {
             const int rel = m.e0 + rel0;
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (rel >> 3);
-            const uint4 *wp = wtab + 2 * ((part * 8 + (rel & 7)) * nv);
+            const uint4 *wp = wtab + 2 * ((part * 8 + (rel & 7)) * p.nt);
             int Um = 0, Nm = 0, Us = 0, Ns = 0, accA = 0;
-            for (int i0 = 0; i0 < nv; i0 += kFlushVecs) {
-                const int i1 = min(nv, i0 + kFlushVecs);
+            if (kNT > 0) {
                 int accM = 0, accS = 0;
-#pragma unroll 3
-                for (int i = i0; i < i1; i++) {
-                    const uint4 dv = dp[i];
+#pragma unroll
+                for (int i = 0; i < kNT; i++) {
+                    uint4 dv = dp[i];
                     const uint4 wv = wp[2 * i];
-                    const uint2 av = *reinterpret_cast<const uint2 *>(wp + 2 * i + 1);
+                    const uint4 av = wp[2 * i + 1];
+                    if (kMerge && i == 0) {
+                        const uint4 tv = dp[kNT];                  // tail vector: slots below e
+                        dv.x = prmt(dv.x, tv.x, av.z);
+                        dv.y = prmt(dv.y, tv.y, av.z >> 16);
+                        dv.z = prmt(dv.z, tv.z, av.w);
+                        dv.w = prmt(dv.w, tv.w, av.w >> 16);
+                    }
                     accum4(dv.x, dv.y, wv.x, wv.z, av.x, k512, accM, accS, accA);
                     accum4(dv.z, dv.w, wv.y, wv.w, av.y, k512, accM, accS, accA);
                 }
                 unpack_acc(accM, Um, Nm);
                 unpack_acc(accS, Us, Ns);
+            } else {
+                for (int i0 = 0; i0 < nv; i0 += kFlushVecs) {
+                    const int i1 = min(nv, i0 + kFlushVecs);
+                    int accM = 0, accS = 0;
+                    for (int i = i0; i < i1; i++) {
+                        const uint4 dv = dp[i];
+                        const uint4 wv = wp[2 * i];
+                        const uint2 av = *reinterpret_cast<const uint2 *>(wp + 2 * i + 1);
+                        accum4(dv.x, dv.y, wv.x, wv.z, av.x, k512, accM, accS, accA);
+                        accum4(dv.z, dv.w, wv.y, wv.w, av.y, k512, accM, accS, accA);
+                    }
+                    unpack_acc(accM, Um, Nm);
+                    unpack_acc(accS, Us, Ns);
+                }
             }
             for (int o = 1; o < tpw; o <<= 1) {
                 Um += __shfl_xor_sync(0xFFFFFFFFu, Um, o);
@@ -552,7 +588,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__re
 }
 
 struct Group {
-    int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, wt = 0, stage_bytes = 0, stages = 0;
+    int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, stage_bytes = 0, stages = 0;
     size_t smem = 0;
     int grid = 0;
     std::vector<int32_t> caps, tile_first;
@@ -560,6 +596,32 @@ struct Group {
 };
 
 }  // namespace
+
+// kernel variants: merge mode with 1..6 vector steps, plain mode with 2..7, generic fallback
+#define AFSK_DEMOD_VARIANTS(X) \
+    X(1, true) X(2, true) X(3, true) X(4, true) X(5, true) X(6, true) \
+    X(2, false) X(3, false) X(4, false) X(5, false) X(6, false) X(7, false) X(0, false)
+
+static cudaError_t demod_set_smem_attr()
+{
+    cudaError_t e = cudaSuccess;
+#define X(NT, MG) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod<NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    AFSK_DEMOD_VARIANTS(X)
+#undef X
+    return e;
+}
+
+static void launch_demod(int merge, int nt, int grid, size_t smem, cudaStream_t st, const DemodParams &p)
+{
+#define X(NT, MG) \
+    if ((MG) == (merge != 0) && (NT) == nt) { k_demod<NT, MG><<<grid, kDemodThreads, smem, st>>>(p); return; }
+    AFSK_DEMOD_VARIANTS(X)
+#undef X
+    DemodParams q = p;          // no specialised variant: generic loop over nv vectors
+    q.merge = 0;
+    k_demod<0, false><<<grid, kDemodThreads, smem, st>>>(q);
+}
 
 struct AfskRxPlan {
     int device = 0;
@@ -578,7 +640,7 @@ struct AfskRxPlan {
 
 static size_t demod_smem_bytes(const Group &g)
 {
-    return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * 8 * g.nv * 32 +
+    return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * 8 * g.nt * 32 +
            kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t) + 2 * kConsumerThreads;
 }
 
@@ -590,6 +652,8 @@ static bool configure_group(Group &g, int bf)
     const int tpw = 1 << g.tpw_log2;
     g.seg = (bf + tpw - 1) / tpw;
     g.nv = (g.seg + 6) / 8 + 1;
+    g.merge = (g.seg % 8 == 0 && g.seg <= 48) ? 1 : 0;   // then bf == tpw * seg and nv == seg/8 + 1
+    g.nt = g.merge ? g.nv - 1 : g.nv;
     g.wt = kConsumerThreads / tpw;
     g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 128) + 127) & ~127;   // copy + over-read slack
     const size_t budget = 100 * 1024;   // two CTAs per SM
@@ -689,8 +753,7 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
         const int per_sm = g.smem <= 113 * 1024 ? 2 : 1;
         g.grid = std::max(1, std::min(total, P->sm_count * per_sm));
     }
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = demod_set_smem_attr();
     if (e != cudaSuccess) {
         afsk_set_error("afsk_rx_plan_create: %s", cudaGetErrorString(e));
         afsk_rx_plan_destroy(P);
@@ -777,12 +840,12 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         p.gcaps = g.d_caps; p.gtile_first = g.d_tile_first;
         p.planes = P->d_planes;
         p.ng = (int)g.caps.size(); p.total_items = g.tile_first.back();
-        p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.wt = g.wt;
+        p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.nt = g.nt; p.merge = g.merge; p.wt = g.wt;
         p.stage_bytes = g.stage_bytes; p.stages = g.stages;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        k_demod<<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);
         if (e0 && e1) {
             cudaEventRecord(e1, st);
             P->timing_events.emplace_back(e0, e1);

@@ -33,6 +33,7 @@ constexpr int kDemodThreads = kConsumerThreads + 32;   // + one producer warp
 constexpr int kMaxStages = 8;
 constexpr int kClockThreads = 128;
 constexpr int kFrameThreads = 128;
+constexpr int kFrameWords = 4;        // plane words per thread per search step
 
 struct __align__(16) CapDesc {
     int64_t off;         // first sample of the capture (global sample index)
@@ -98,70 +99,108 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
         }
         return;
     }
-    // y = 4104 samples starting at the 16-byte boundary at or below the capture start
-    __shared__ uint32_t P[AFSK_SYNC_FRAMES + 8 + 1];   // P[i] = sum y[0..i)  (mod 2^32)
+    // y = up to 4104 samples starting at the 16-byte boundary at or below the capture start.
+    // Qs[4 + i] = y[0] + ... + y[i] (mod 2^32), Qs[3] = 0, so P[i] = sum y[0..i) = Qs[3 + i].
+    __shared__ __align__(16) uint32_t Qs[4 + AFSK_SYNC_FRAMES + 8];
     __shared__ uint32_t warp_tot[kClockThreads / 32];
     __shared__ uint32_t warp_min[kClockThreads / 32];
+    const uint32_t *P = Qs + 3;
     const int64_t ga = d.off & ~(int64_t)7;
     const int e = (int)(d.off - ga);
     const uint4 *src = reinterpret_cast<const uint4 *>(x + ga);
-    // 128*4 = 512 vectors cover the scan when the capture is 16-byte aligned; one more otherwise
-    const int nvec = (tid == kClockThreads - 1 && e > 0) ? 5 : 4;
-    int32_t loc[40];
-    uint32_t run = 0;
+    // warp w scans samples [1024w, 1024w + 1024): 4 rounds of 32 coalesced 16-byte vectors
+    uint32_t pre[4][8], vsum[4], voff[4];
 #pragma unroll
-    for (int v = 0; v < 5; v++) {
-        if (v < nvec) {
-            uint4 q = ld_nc_v4(src + tid * 4 + v);
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    for (int r = 0; r < 4; r++) {
+        const uint4 qv = ld_nc_v4(src + warp * 128 + r * 32 + lane);
+        const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
+        uint32_t run = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int lo = (int)(int16_t)(w[j] & 0xFFFF), hi = (int)(int16_t)(w[j] >> 16);
-                run += (uint32_t)lo; loc[v * 8 + 2 * j] = (int32_t)run;
-                run += (uint32_t)hi; loc[v * 8 + 2 * j + 1] = (int32_t)run;
-            }
+        for (int j = 0; j < 4; j++) {
+            run += (uint32_t)(int)(int16_t)(wv[j] & 0xFFFF); pre[r][2 * j] = run;
+            run += (uint32_t)(int)(int16_t)(wv[j] >> 16);    pre[r][2 * j + 1] = run;
+        }
+        vsum[r] = run;
+    }
+    uint32_t carry = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        uint32_t inc = vsum[r];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        voff[r] = carry + inc - vsum[r];
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    }
+    if (lane == 0) warp_tot[warp] = carry;
+    if (tid == 0) Qs[3] = 0;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; w++) base += warp_tot[w];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint32_t o = base + voff[r];
+        uint4 *dst = reinterpret_cast<uint4 *>(Qs + 4 + (warp * 128 + r * 32 + lane) * 8);
+        dst[0] = make_uint4(o + pre[r][0], o + pre[r][1], o + pre[r][2], o + pre[r][3]);
+        dst[1] = make_uint4(o + pre[r][4], o + pre[r][5], o + pre[r][6], o + pre[r][7]);
+    }
+    if (tid == kClockThreads - 1 && e > 0) {
+        // an unaligned capture start needs the 513th vector (samples 4096..4103 of y)
+        const uint4 qv = ld_nc_v4(src + 512);
+        const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
+        uint32_t run = base + carry;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            run += (uint32_t)(int)(int16_t)(wv[j] & 0xFFFF); Qs[4 + 4096 + 2 * j] = run;
+            run += (uint32_t)(int)(int16_t)(wv[j] >> 16);    Qs[4 + 4096 + 2 * j + 1] = run;
         }
     }
-    // exclusive scan of the per-thread totals
-    uint32_t inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    uint32_t base = inc - run;
-    for (int w = 0; w < warp; w++) base += warp_tot[w];
-    if (tid == 0) P[0] = 0;
-#pragma unroll
-    for (int v = 0; v < 5; v++)
-        if (v < nvec)
-#pragma unroll
-            for (int k = 0; k < 8; k++) P[(tid * 4 + v) * 8 + k + 1] = base + (uint32_t)loc[v * 8 + k];
     __syncthreads();
 
     const int bf = d.bf, q = bf >> 2, h = bf >> 1;
     const int span = AFSK_SYNC_FRAMES - 2 * bf;                 // :327
     const uint32_t c0 = 65535u * (uint32_t)bf;
     const uint32_t div = 2u * (uint32_t)bf;
+    // getDiff(i) = floor(D_i / 2bf) is monotone in D_i, so the first strict minimum (:332-337) is the
+    // first i with D_i <= T where T = (floor(min D / 2bf) + 1) * 2bf - 1: one division per capture.
+    constexpr int kPerThread = AFSK_SYNC_FRAMES / kClockThreads;   // 32 candidates per thread at most
+    uint32_t Dv[kPerThread];
     uint32_t best = 0xFFFFFFFFu;
-    for (int i = tid; i < span; i += kClockThreads) {
-        const int b = i + e;
-        // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO)
-        uint32_t D = c0 + P[b] - 2u * P[b + q] + 2u * P[b + 2 * q] - 2u * P[b + 3 * q] + 2u * P[b + bf] -
-                     2u * P[b + bf + h] + P[b + 2 * bf];
-        uint32_t dq = D / div;                                  // getDiff :107
-        uint32_t key = (dq << 12) | (uint32_t)i;                // first strict minimum :332-337
-        best = min(best, key);
+#pragma unroll
+    for (int k = 0; k < kPerThread; k++) {
+        const int i = tid + k * kClockThreads;
+        uint32_t D = 0xFFFFFFFFu;
+        if (i < span) {
+            const int b = i + e;
+            // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO)
+            D = c0 + P[b] - 2u * P[b + q] + 2u * P[b + 2 * q] - 2u * P[b + 3 * q] + 2u * P[b + bf] -
+                2u * P[b + bf + h] + P[b + 2 * bf];
+        }
+        Dv[k] = D;
+        best = min(best, D);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
     if (lane == 0) warp_min[warp] = best;
     __syncthreads();
+    best = warp_min[0];
+#pragma unroll
+    for (int w = 1; w < kClockThreads / 32; w++) best = min(best, warp_min[w]);
+    const uint32_t T = (best / div + 1u) * div - 1u;            // getDiff :107
+    uint32_t first = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = kPerThread - 1; k >= 0; k--)
+        if (Dv[k] <= T) first = (uint32_t)(tid + k * kClockThreads);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+    __syncthreads();
+    if (lane == 0) warp_min[warp] = first;
+    __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < kClockThreads / 32; w++) best = min(best, warp_min[w]);
-        clock[c] = (int32_t)(best & 0xFFFu);
+        for (int w = 1; w < kClockThreads / 32; w++) first = min(first, warp_min[w]);
+        clock[c] = (int32_t)first;
     }
 }
 
@@ -472,15 +511,18 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
 
     // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
     long long kterm = NONE;
-    for (long long base = 0; base < nwords; base += kFrameThreads) {
-        const long long j = base + tid;
+    for (long long base = 0; base < nwords; base += kFrameThreads * kFrameWords) {
         long long cand = NONE;
-        if (j < nwords) {
-            const uint64_t v = ((uint64_t)PL[j].x << 32) | (j ? PL[j - 1].x : 0u);
-            uint32_t M = (uint32_t)((v >> 29) & ~(v >> 30) & ~(v >> 31) & ~(v >> 32));
-            const long long rem = K - 32 * j;
-            if (rem < 32) M &= (1u << rem) - 1u;
-            if (M) cand = 32 * j + (__ffs(M) - 1);
+#pragma unroll
+        for (int r = kFrameWords - 1; r >= 0; r--) {
+            const long long j = base + tid + r * kFrameThreads;
+            if (j < nwords) {
+                const uint64_t v = ((uint64_t)PL[j].x << 32) | (j ? PL[j - 1].x : 0u);
+                uint32_t M = (uint32_t)((v >> 29) & ~(v >> 30) & ~(v >> 31) & ~(v >> 32));
+                const long long rem = K - 32 * j;
+                if (rem < 32) M &= (1u << rem) - 1u;
+                if (M) cand = 32 * j + (__ffs(M) - 1);
+            }
         }
         kterm = block_min_ll(cand, scratch);
         if (kterm != NONE) break;
@@ -488,15 +530,18 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
     const long long k0 = (kterm == NONE) ? K : kterm + 1;
     // phase 2 (:372-378): first quiet window at or after k0
     long long k1 = NONE;
-    for (long long base = k0 >> 5; base < nwords; base += kFrameThreads) {
-        const long long j = base + tid;
+    for (long long base = k0 >> 5; base < nwords; base += kFrameThreads * kFrameWords) {
         long long cand = NONE;
-        if (j < nwords) {
-            uint32_t M = PL[j].y;
-            if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
-            const long long rem = K - 32 * j;
-            if (rem < 32) M &= (1u << rem) - 1u;
-            if (M) cand = 32 * j + (__ffs(M) - 1);
+#pragma unroll
+        for (int r = kFrameWords - 1; r >= 0; r--) {
+            const long long j = base + tid + r * kFrameThreads;
+            if (j < nwords) {
+                uint32_t M = PL[j].y;
+                if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
+                const long long rem = K - 32 * j;
+                if (rem < 32) M &= (1u << rem) - 1u;
+                if (M) cand = 32 * j + (__ffs(M) - 1);
+            }
         }
         k1 = block_min_ll(cand, scratch);
         if (k1 != NONE) break;

@@ -283,6 +283,30 @@ class Receiver:
         self._amp_end = amp_end_threshold
         self._device = device
         self._log = Log("afskmodem.Receiver")
+        self._cache = None                                       # (key, RxSession) of the last batch layout
+
+    def _session(self, offsets: np.ndarray, dev: int) -> RxSession:
+        """Plan + device buffers are kept between calls with the same batch layout (like an FFT
+        plan cache): repeated decode_batch calls then pay only H2D, kernels and D2H."""
+        key = (dev, self._baud, _as_int_threshold(self._amp_end), offsets.tobytes())
+        if self._cache is not None and self._cache[0] == key:
+            return self._cache[1]
+        self.close()
+        s = RxSession(offsets, self._baud, _as_int_threshold(self._amp_end), dev)
+        self._cache = (key, s)
+        return s
+
+    def close(self):
+        """Releases the cached plan and device buffers."""
+        if getattr(self, "_cache", None) is not None:
+            self._cache[1].close()
+            self._cache = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
     # -- batch API -------------------------------------------------------------------------
     def decode_batch(self, samples, offsets=None, device: int | None = None) -> RxBatch:
@@ -292,13 +316,10 @@ class Receiver:
         if offsets is None:
             samples, offsets = _concat(samples)
         dev = self._device if device is None else device
-        s = RxSession(offsets, self._baud, _as_int_threshold(self._amp_end), dev)
-        try:
-            s.upload(samples)
-            s.run()
-            return s.download()
-        finally:
-            s.close()
+        s = self._session(np.ascontiguousarray(offsets, dtype=np.int64), dev)
+        s.upload(samples)
+        s.run()
+        return s.download()
 
     def to_python(self, batch: RxBatch, i: int, string: bool = True, log: bool = True):
         """Capture i of a batch as ``load`` would have returned it (F8 return-type rules), with the

@@ -250,6 +250,23 @@ __device__ __forceinline__ void unpack_acc(int acc, int &U, int &Xn)
     Xn += (acc - u) >> 8;
 }
 
+// keep every 2nd / 4th bit of a ballot, packed to the low 16 / 8 bits
+__device__ __forceinline__ uint32_t squeeze2(uint32_t x)
+{
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    return (x | (x >> 8)) & 0xFFFFu;
+}
+__device__ __forceinline__ uint32_t squeeze4(uint32_t x)
+{
+    x &= 0x11111111u;
+    x = (x | (x >> 3)) & 0x03030303u;
+    x = (x | (x >> 6)) & 0x000F000Fu;
+    return (x | (x >> 12)) & 0xFFu;
+}
+
 constexpr int kFlushVecs = 15;      // 120 samples: keeps |T.c| <= 127 inside one packed accumulator
 
 // kNT > 0: the number of vector steps per thread is a compile-time constant (fully unrolled, one
@@ -265,8 +282,11 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     const int tpw = 1 << p.tpw_log2;
     uint8_t *stage_base = smem;
     uint4 *wtab = reinterpret_cast<uint4 *>(smem + (size_t)S * p.stage_bytes);
-    const int wtab_entries = tpw * 8 * p.nt;                       // 32 bytes each
-    TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + 2 * wtab_entries);
+    // entry (part, e, i) = two uint4 at wtab[part * PSq + e * ESq + 2 * i]; the odd strides put the
+    // entries that the lanes of one warp read together (different part / e) in different banks
+    const int wtab_entries = tpw * 8 * p.nt;
+    const int ESq = 2 * p.nt + 1, PSq = 8 * ESq + 1;
+    TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + tpw * PSq);
     uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
     uint64_t *empty = full + kMaxStages;
     uint8_t *resbuf = reinterpret_cast<uint8_t *>(empty + kMaxStages);   // [2][kConsumerThreads]
@@ -300,8 +320,9 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
                 const uint32_t sj = (2 * j >= e) ? 0x3210u : ((2 * j + 1 < e) ? 0x7654u : 0x3254u);
                 sel[j >> 1] |= sj << (16 * (j & 1));
             }
-            wtab[2 * idx] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
-            wtab[2 * idx + 1] = make_uint4(in[0], in[1], sel[0], sel[1]);
+            uint4 *ent = wtab + part * PSq + e * ESq + 2 * i;
+            ent[0] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
+            ent[1] = make_uint4(in[0], in[1], sel[0], sel[1]);
         }
     }
     if (tid == 0) {
@@ -392,7 +413,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
         if (m.nwin > 0) {
             const int rel = m.e0 + rel0;
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (rel >> 3);
-            const uint4 *wp = wtab + 2 * ((part * 8 + (rel & 7)) * p.nt);
+            const uint4 *wp = wtab + part * PSq + (rel & 7) * ESq;
             int Um = 0, Nm = 0, Us = 0, Ns = 0, accA = 0;
             if (kNT > 0) {
                 int accM = 0, accS = 0;
@@ -452,6 +473,26 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
                 const uint32_t bw = __ballot_sync(0xFFFFFFFFu, bit);
                 const uint32_t qw = __ballot_sync(0xFFFFFFFFu, quiet);
                 if (lane == 0 && warp * 32 < m.nwin) p.planes[m.word_base + warp] = make_uint2(bw, qw);
+            } else if (p.tpw_log2 <= 2) {
+                // 2 or 4 threads per window: the part-0 lanes hold the decisions; squeeze the
+                // stride-tpw ballot into 16 / 8 bits and store them as a sub-word of the plane
+                // (no CTA-wide barrier on this path)
+                uint32_t bw = __ballot_sync(0xFFFFFFFFu, bit);
+                uint32_t qw = __ballot_sync(0xFFFFFFFFu, quiet);
+                const int per_warp = 32 >> p.tpw_log2;
+                const int w0 = warp * per_warp;
+                if (lane == 0 && w0 < m.nwin) {
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(p.planes + m.word_base + (w0 >> 5)) + ((w0 & 31) >> 3);
+                    if (p.tpw_log2 == 1) {
+                        bw = squeeze2(bw); qw = squeeze2(qw);
+                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)bw;
+                        *reinterpret_cast<uint16_t *>(dst + 4) = (uint16_t)qw;
+                    } else {
+                        bw = squeeze4(bw); qw = squeeze4(qw);
+                        dst[0] = (uint8_t)bw;
+                        dst[4] = (uint8_t)qw;
+                    }
+                }
             } else {
                 uint8_t *rb = resbuf + (n & 1) * kConsumerThreads;
                 if (part == 0) rb[w] = (uint8_t)((bit ? 1 : 0) | (quiet ? 2 : 0));
@@ -685,7 +726,7 @@ struct AfskRxPlan {
 
 static size_t demod_smem_bytes(const Group &g)
 {
-    return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * 8 * g.nt * 32 +
+    return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * (8 * (2 * g.nt + 1) + 1) * 16 +
            kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t) + 2 * kConsumerThreads;
 }
 

@@ -39,13 +39,26 @@ sys.path.insert(0, ROOT)
 BAUD = 1200
 PAYLOAD = 1024
 AMP_END = 14000
+# other BASELINE configs, for tuning runs only (the bench line of record is c2):
+#   c3: 6000 baud stand-in for the reference-unsupported 9600, 16384 x 1 KB
+#   c4: 300 baud, 64 KB payloads, 64 captures of 146.8 M samples
+WORKLOADS = {"c2": (1200, 1024, 4096), "c3": (6000, 1024, 16384), "c4": (300, 65536, 64)}
 SIGMAS = np.array([0, 2000, 8000, 14000, 19000, 26000], dtype=np.float64)
 SIGMA_W = np.array([1, 2, 3, 2, 1, 1], dtype=np.float64) / 10.0
 CLEAN_N = 602400                 # frames Transmitter(1200).save writes for 1 KB
+WL = "c2"
+
+
+def set_workload(name, captures):
+    global BAUD, PAYLOAD, CLEAN_N, WL
+    WL = name
+    BAUD, PAYLOAD, default_b = WORKLOADS[name]
+    CLEAN_N = (2 * int(BAUD * 0.5 / 2) + 4 + 14 * PAYLOAD) * (48000 // BAUD) + 4800
+    return captures if captures else default_b
 
 
 def workload_name(B):
-    return f"c2: {B} x 1200-baud captures, 1 KB payload, AWGN mix, 25% lead silence"
+    return f"{WL}: {B} x {BAUD}-baud captures, {PAYLOAD} B payload, AWGN mix, 25% lead silence"
 
 
 def capture_recipe(B, rank):
@@ -116,7 +129,7 @@ def build_batch_on_gpu(B, rank, device):
     samples = torch.zeros(total + 64, dtype=torch.int16, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    chunk = 128
+    chunk = max(1, min(128, (1 << 27) // CLEAN_N))
     for c0 in range(0, B, chunk):
         c1 = min(B, c0 + chunk)
         for c in range(c0, c1):
@@ -190,13 +203,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--captures", type=int, default=4096, help="captures per GPU")
+    ap.add_argument("--captures", type=int, default=0, help="captures per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-captures", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.captures = set_workload(args.workload, args.captures)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -230,7 +245,7 @@ def main():
     parity_checked = 0
     if rank == 0:
         from oracle import oracle as O
-        picks = sorted(set([0, 1, 2, 3, B // 2, B - 1] + [int(np.argmax(sigma == s)) for s in SIGMAS if (sigma == s).any()]))
+        picks = sorted(set([0, 1, 2, 3, B // 2, B - 1][:6 if WL != "c4" else 2] + [int(np.argmax(sigma == s)) for s in SIGMAS if (sigma == s).any()]))
         for c in picks:
             x = samples[int(offsets[c]):int(offsets[c + 1])].cpu().numpy()
             o = O.rx_decode(x, BAUD, AMP_END)

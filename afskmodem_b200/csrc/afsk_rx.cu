@@ -32,8 +32,7 @@ constexpr int kConsumerThreads = 256;
 constexpr int kDemodThreads = kConsumerThreads + 32;   // + one producer warp
 constexpr int kMaxStages = 8;
 constexpr int kClockThreads = 128;
-constexpr int kFrameThreads = 128;
-constexpr int kFrameWords = 4;        // plane words per thread per search step
+constexpr int kFrameThreads = 128;    // k_gate_scan block; k_frame is templated on its own block size
 
 struct __align__(16) CapDesc {
     int64_t off;         // first sample of the capture (global sample index)
@@ -510,6 +509,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
 }
 
 // ------------------------------------------------------------------------------ k_frame ----
+template <int kThreads>
 __device__ __forceinline__ long long block_min_ll(long long v, long long *scratch)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -519,7 +519,8 @@ __device__ __forceinline__ long long block_min_ll(long long v, long long *scratc
     if (lane == 0) scratch[warp] = v;
     __syncthreads();
     long long r = scratch[0];
-    for (int w = 1; w < kFrameThreads / 32; w++) r = min(r, scratch[w]);
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; w++) r = min(r, scratch[w]);
     return r;
 }
 
@@ -534,7 +535,10 @@ __device__ __forceinline__ uint32_t hamming74_nibble(uint32_t cw)
     return (((cw >> 2) & 1u) << 3) | (((cw >> 4) & 1u) << 2) | (((cw >> 5) & 1u) << 1) | ((cw >> 6) & 1u);
 }
 
-__global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restrict__ caps,
+// kThreads x kWords plane words are searched per block step: <128,4> for ordinary captures,
+// <512,8> when a capture has more than 16384 windows (e.g. 64 KB payloads at 300 baud).
+template <int kThreads, int kWords>
+__global__ void __launch_bounds__(kThreads) k_frame(const CapDesc *__restrict__ caps,
                                                          const int32_t *__restrict__ clock,
                                                          const uint2 *__restrict__ planes,
                                                          uint8_t *__restrict__ out,
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
     const int c = blockIdx.x, tid = threadIdx.x;
     const CapDesc d = caps[c];
     if (d.status0 != 0) return;
-    __shared__ long long scratch[kFrameThreads / 32];
+    __shared__ long long scratch[kThreads / 32];
     const int clk = clock[c];
     const long long K = num_windows(d.n, d.bf, clk);
     const long long nwords = (K + 31) >> 5;
@@ -552,11 +556,11 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
 
     // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
     long long kterm = NONE;
-    for (long long base = 0; base < nwords; base += kFrameThreads * kFrameWords) {
+    for (long long base = 0; base < nwords; base += kThreads * kWords) {
         long long cand = NONE;
 #pragma unroll
-        for (int r = kFrameWords - 1; r >= 0; r--) {
-            const long long j = base + tid + r * kFrameThreads;
+        for (int r = kWords - 1; r >= 0; r--) {
+            const long long j = base + tid + r * kThreads;
             if (j < nwords) {
                 const uint64_t v = ((uint64_t)PL[j].x << 32) | (j ? PL[j - 1].x : 0u);
                 uint32_t M = (uint32_t)((v >> 29) & ~(v >> 30) & ~(v >> 31) & ~(v >> 32));
@@ -565,17 +569,17 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
                 if (M) cand = 32 * j + (__ffs(M) - 1);
             }
         }
-        kterm = block_min_ll(cand, scratch);
+        kterm = block_min_ll<kThreads>(cand, scratch);
         if (kterm != NONE) break;
     }
     const long long k0 = (kterm == NONE) ? K : kterm + 1;
     // phase 2 (:372-378): first quiet window at or after k0
     long long k1 = NONE;
-    for (long long base = k0 >> 5; base < nwords; base += kFrameThreads * kFrameWords) {
+    for (long long base = k0 >> 5; base < nwords; base += kThreads * kWords) {
         long long cand = NONE;
 #pragma unroll
-        for (int r = kFrameWords - 1; r >= 0; r--) {
-            const long long j = base + tid + r * kFrameThreads;
+        for (int r = kWords - 1; r >= 0; r--) {
+            const long long j = base + tid + r * kThreads;
             if (j < nwords) {
                 uint32_t M = PL[j].y;
                 if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
@@ -584,14 +588,15 @@ __global__ void __launch_bounds__(kFrameThreads) k_frame(const CapDesc *__restri
                 if (M) cand = 32 * j + (__ffs(M) - 1);
             }
         }
-        k1 = block_min_ll(cand, scratch);
+        k1 = block_min_ll<kThreads>(cand, scratch);
         if (k1 != NONE) break;
     }
     if (k1 == NONE) k1 = K;
     const long long nbits = k1 - k0;
     const long long nbytes = (nbits / 7) / 2;        // ECC.decode :156, __bitsToBytes :396
     uint8_t *o = out + d.out_off;
-    for (long long i = tid; i < nbytes; i += kFrameThreads) {
+#pragma unroll 4
+    for (long long i = tid; i < nbytes; i += kThreads) {
         const long long pos = k0 + 14 * i;
         const uint32_t lo = PL[pos >> 5].x, hi = PL[(pos >> 5) + 1].x;
         const uint32_t val = __funnelshift_r(lo, hi, (uint32_t)(pos & 31));
@@ -650,7 +655,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__re
     for (long long base = 1; base <= last; base += kFrameThreads) {
         const long long j = base + tid;
         long long cand = (j <= last && A[j] > amp_start) ? j : NONE;     // :306
-        open = block_min_ll(cand, scratch);
+        open = block_min_ll<kFrameThreads>(cand, scratch);
         if (open != NONE) break;
     }
     long long close = NONE;
@@ -658,7 +663,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__re
         for (long long base = open + 1; base < nch; base += kFrameThreads) {
             const long long j = base + tid;
             long long cand = (j < nch && A[j] < amp_end) ? j : NONE;     // :316
-            close = block_min_ll(cand, scratch);
+            close = block_min_ll<kFrameThreads>(cand, scratch);
             if (close != NONE) break;
         }
     }
@@ -720,6 +725,7 @@ struct AfskRxPlan {
     int32_t *d_clock = nullptr;
     uint2 *d_planes = nullptr;
     int64_t plane_words = 0;
+    int64_t max_windows = 0;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
@@ -814,6 +820,7 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
             d.group = it->second;
             const int64_t kmax = (d.n - bf + bf - 1) / bf;             // windows at clock 0
             const int64_t ntiles = (kmax + g.wt - 1) / g.wt;
+            P->max_windows = std::max(P->max_windows, kmax);
             if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
             g.caps.push_back(c);
             g.tile_first.push_back(g.tile_first.back() + (int32_t)ntiles);
@@ -937,7 +944,10 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
             P->timing_events.emplace_back(e0, e1);
         }
     }
-    k_frame<<<P->B, kFrameThreads, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
+    if (P->max_windows > 16384)
+        k_frame<512, 8><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
+    else
+        k_frame<128, 4><<<P->B, 128, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     AFSK_CUDA(cudaGetLastError());
     return AFSK_OK;
 }

@@ -18,15 +18,16 @@
 namespace {
 
 constexpr int kSynthThreads = 256;
-constexpr int kVecPerThread = 4;
-constexpr int kChunkVecs = kSynthThreads * kVecPerThread;   // 1024 vectors = 8192 samples per CTA
+constexpr int kVecPerThread = 32;
+constexpr int kChunkVecs = kSynthThreads * kVecPerThread;   // 8192 vectors = 65536 samples per CTA
+constexpr int kMaxSymbols = kChunkVecs * 8 / 4 + 8;         // bit symbols one chunk can touch (bf >= 4)
 
 struct __align__(16) TxDesc {
     int64_t pay_off;      // byte offset of the payload
     int64_t pay_len;
     int64_t out_off;      // sample offset of the capture (multiple of 8)
     int64_t out_len;      // frames written by save(): (len(frames) & ~1)
-    int64_t sig_frames;   // frames before the zero tail = total_bits * bf
+    int64_t total_bits;   // training + terminator + coded bits
     int64_t ts_bits;      // 2 * ts_cycles training bits (1,0,1,0,...)
     int32_t bf;
     int32_t pad;
@@ -41,6 +42,7 @@ __device__ __forceinline__ uint32_t hamming74_encode(uint32_t v)
            (d3 << 6);
 }
 
+// bit b of the transmitted sequence (__getFrames :452-469)
 __device__ __forceinline__ uint32_t tx_bit(long long b, const TxDesc &d, const uint8_t *__restrict__ pay)
 {
     if (b < d.ts_bits) return (uint32_t)(~b & 1);            // training cycle = mark, space  :457-458
@@ -55,55 +57,84 @@ __device__ __forceinline__ uint32_t tx_bit(long long b, const TxDesc &d, const u
 }
 
 // frame value at phase ph of a tone (Waveforms.getSpaceTone/getMarkTone :68-85), as 2 duplicated
-// int16 (SoundOutput.__convertFrames emits every even frame twice)
-__device__ __forceinline__ uint32_t tone_pair(uint32_t bit, int ph, int bf)
+// int16 (SoundOutput.__convertFrames :239-244 emits every even frame twice); sym 2 = silence
+__device__ __forceinline__ uint32_t tone_pair(uint32_t sym, int ph, int bf)
 {
+    if (sym == 2u) return 0u;
     const int q = bf >> 2, h = bf >> 1;
     bool hi;
-    if (bit) hi = (ph < q) || (ph >= h && ph < h + q);       // mark : q HI, q LO, q HI, q LO
+    if (sym) hi = (ph < q) || (ph >= h && ph < h + q);       // mark : q HI, q LO, q HI, q LO
     else hi = ph < h;                                        // space: h HI, h LO
     return hi ? 0x7FFF7FFFu : 0x80008000u;
 }
 
+// One CTA writes 8192 consecutive 16-byte vectors of one capture.  Bits are grouped so that a group
+// is a whole number of vectors (1 bit when bf % 8 == 0, else 2 bits); the CTA tabulates the vector
+// patterns of every symbol combination of a group (3 or 9 combinations: space / mark / silence)
+// and the bit symbols its chunk touches in shared memory, then every thread emits
+// pattern[combination][vector-in-group] with one 128-bit shared load and one coalesced 128-bit store.
 __global__ void __launch_bounds__(kSynthThreads) k_synth(const uint8_t *__restrict__ pay,
-                                                         const TxDesc *__restrict__ descs, int B,
+                                                         const TxDesc *__restrict__ descs,
+                                                         const int32_t *__restrict__ chunk_cap,
                                                          int16_t *__restrict__ out)
 {
-    // capture of this chunk
+    extern __shared__ __align__(16) uint8_t tx_smem[];
+    const int tid = threadIdx.x;
     const long long chunk = blockIdx.x;
-    int a = 0, b = B;
-    while (b - a > 1) {
-        const int mid = (a + b) >> 1;
-        if (descs[mid].chunk_first <= chunk) a = mid; else b = mid;
-    }
-    const TxDesc d = descs[a];
-    const long long nvec_cap = (d.out_len + 7) >> 3;          // vectors of this capture (last one zero padded)
+    const TxDesc d = descs[chunk_cap[chunk]];
+    const int bf = d.bf;
+    const int G = (bf & 7) ? 2 : 1;                          // bits per group
+    const int VG = G * bf / 8;                               // vectors per group
+    const int ncomb = G == 1 ? 3 : 9;
+    uint4 *tab = reinterpret_cast<uint4 *>(tx_smem);
+    uint8_t *sym = tx_smem + (size_t)ncomb * VG * 16;
+
+    const long long nvec_cap = (d.out_len + 7) >> 3;
     const long long v0 = (chunk - d.chunk_first) * kChunkVecs;
-    uint4 *dst = reinterpret_cast<uint4 *>(out + d.out_off);
-#pragma unroll
-    for (int r = 0; r < kVecPerThread; r++) {
-        const long long vi = v0 + r * kSynthThreads + threadIdx.x;
-        if (vi >= nvec_cap) break;
-        const long long n0 = vi * 8;
-        long long bidx = n0 / d.bf;
-        int ph = (int)(n0 - bidx * d.bf);
-        uint32_t bit = (n0 < d.sig_frames) ? tx_bit(bidx, d, pay) : 0u;
+    const long long vend = min(v0 + (long long)kChunkVecs, nvec_cap);
+    const long long g0 = v0 / VG, g1 = (vend - 1) / VG;
+    const long long b0 = g0 * G;
+    const int nb = (int)(g1 - g0 + 1) * G;
+    for (int i = tid; i < nb; i += kSynthThreads) {
+        const long long bi = b0 + i;
+        sym[i] = bi < d.total_bits ? (uint8_t)tx_bit(bi, d, pay) : (uint8_t)2;    // 4800 zero frames :468
+    }
+    for (int idx = tid; idx < ncomb * VG; idx += kSynthThreads) {
+        const int comb = idx / VG, k = idx - comb * VG;
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const long long n = n0 + 2 * j;
-            uint32_t val = 0u;
-            if (n < d.out_len && n < d.sig_frames) val = tone_pair(bit, ph, d.bf);
-            w[j] = val;
-            ph += 2;
-            if (ph >= d.bf) {
-                ph -= d.bf;
-                bidx++;
-                if (n + 2 < d.sig_frames) bit = tx_bit(bidx, d, pay);
+            int n = 8 * k + 2 * j;                           // even frame inside the group
+            uint32_t s = (uint32_t)comb;
+            if (G == 2) {
+                if (n >= bf) { n -= bf; s = comb % 3; } else s = comb / 3;
             }
+            w[j] = tone_pair(s, n, bf);
         }
-        dst[vi] = make_uint4(w[0], w[1], w[2], w[3]);
+        tab[idx] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    __syncthreads();
+
+    uint4 *dst = reinterpret_cast<uint4 *>(out + d.out_off);
+    const int vr0 = (int)(v0 - g0 * VG) + tid;               // vector index relative to group g0
+    int gi = vr0 / VG, k = vr0 - gi * VG;
+    const int dg = kSynthThreads / VG, dk = kSynthThreads - dg * VG;
+#pragma unroll 8
+    for (int r = 0; r < kVecPerThread; r++) {
+        const long long vi = v0 + r * kSynthThreads + tid;
+        if (vi < vend) {
+            const int comb = G == 1 ? sym[gi] : sym[2 * gi] * 3 + sym[2 * gi + 1];
+            dst[vi] = tab[comb * VG + k];
+        }
+        gi += dg; k += dk;
+        if (k >= VG) { k -= VG; gi++; }
+    }
+}
+
+static size_t synth_smem_bytes(int bf)
+{
+    const int G = (bf & 7) ? 2 : 1, VG = G * bf / 8;
+    return (size_t)(G == 1 ? 3 : 9) * VG * 16 + kMaxSymbols;
 }
 
 }  // namespace
@@ -114,7 +145,10 @@ struct AfskTxPlan {
     std::vector<TxDesc> descs;
     std::vector<int64_t> out_off, out_len;
     TxDesc *d_descs = nullptr;
+    int32_t *d_chunk_cap = nullptr;
+    std::vector<int32_t> chunk_cap;
     int64_t total_chunks = 0;
+    size_t smem = 0;
 };
 
 extern "C" {
@@ -174,19 +208,28 @@ int afsk_tx_plan_create(int device, int B, const int64_t *h_pay_off, const int32
         if (d.pay_len < 0) { delete P; afsk_set_error("payload offsets must be non-decreasing"); return AFSK_E_ARG; }
         d.bf = bf; d.pad = 0;
         d.ts_bits = 2 * ts;
-        d.sig_frames = (d.ts_bits + 4 + 14 * d.pay_len) * bf;
-        d.out_len = (d.sig_frames + AFSK_TAIL_FRAMES) & ~(int64_t)1;
+        d.total_bits = d.ts_bits + 4 + 14 * d.pay_len;
+        d.out_len = (d.total_bits * bf + AFSK_TAIL_FRAMES) & ~(int64_t)1;
+        P->smem = std::max(P->smem, synth_smem_bytes(bf));
         d.out_off = P->out_off[c];
         d.chunk_first = chunks;
         const int64_t nvec = (d.out_len + 7) >> 3;
-        chunks += (nvec + kChunkVecs - 1) / kChunkVecs;
+        const int64_t nch = (nvec + kChunkVecs - 1) / kChunkVecs;
+        if (chunks + nch > 0x7FFFFFF0LL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
+        P->chunk_cap.insert(P->chunk_cap.end(), (size_t)nch, (int32_t)c);
+        chunks += nch;
         P->out_len[c] = d.out_len;
         P->out_off[c + 1] = P->out_off[c] + nvec * 8;
     }
     P->total_chunks = chunks;
     if (chunks > 0x7FFFFFFFLL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
+    if (P->smem > 200 * 1024) { delete P; afsk_set_error("bit_frames too large for the synthesizer"); return AFSK_E_UNSUPPORTED; }
     cudaError_t e = cudaMalloc((void **)&P->d_descs, sizeof(TxDesc) * (B ? B : 1));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess && B) e = cudaMemcpy(P->d_descs, P->descs.data(), sizeof(TxDesc) * B, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_chunk_cap, sizeof(int32_t) * (chunks ? chunks : 1));
+    if (e == cudaSuccess && chunks)
+        e = cudaMemcpy(P->d_chunk_cap, P->chunk_cap.data(), sizeof(int32_t) * chunks, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         afsk_set_error("afsk_tx_plan_create: %s", cudaGetErrorString(e));
         afsk_tx_plan_destroy(P);
@@ -201,6 +244,7 @@ int afsk_tx_plan_destroy(AfskTxPlan *P)
     if (!P) return AFSK_OK;
     AfskDeviceGuard guard(P->device);
     cudaFree(P->d_descs);
+    cudaFree(P->d_chunk_cap);
     delete P;
     return AFSK_OK;
 }
@@ -220,7 +264,7 @@ int afsk_tx_synth(AfskTxPlan *P, const uint8_t *d_payload, int16_t *d_out, void 
     if (P->B == 0 || P->total_chunks == 0) return AFSK_OK;
     AfskDeviceGuard guard(P->device);
     if (!guard.ok) return AFSK_E_CUDA;
-    k_synth<<<(unsigned)P->total_chunks, kSynthThreads, 0, (cudaStream_t)stream>>>(d_payload, P->d_descs, P->B, d_out);
+    k_synth<<<(unsigned)P->total_chunks, kSynthThreads, P->smem, (cudaStream_t)stream>>>(d_payload, P->d_descs, P->d_chunk_cap, d_out);
     AFSK_CUDA(cudaGetLastError());
     return AFSK_OK;
 }

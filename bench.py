@@ -330,16 +330,21 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-    demod_avg_ms = demod_ms / max(demod_launches, 1)
-    achieved = 2.0 * total / (demod_avg_ms / 1000) / 1e9
+    # k_demod time per decode = span from the first to the last k_demod launch of each decode call
+    # (the launches of the capture ranges run back to back); achieved = bytes per decode / that
+    demod_per_decode_ms = demod_ms / args.steps
+    launches_per_decode = max(demod_launches, 1) / args.steps
+    demod_avg_ms = demod_per_decode_ms / launches_per_decode
+    achieved = 2.0 * total / (demod_per_decode_ms / 1000) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("k_demod_c2_dram_bytes_per_launch")
     roofline = {"kernel": "k_demod", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": 2 * total, "avg_launch_ms": demod_avg_ms,
-                "share_of_step": demod_avg_ms / (elapsed_ms / args.steps)}
+                "algorithmic_bytes_per_launch": 2 * total / launches_per_decode, "avg_launch_ms": demod_avg_ms,
+                "launches_per_step": launches_per_decode,
+                "share_of_step": demod_per_decode_ms / (elapsed_ms / args.steps)}
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample ----
     cpu = None

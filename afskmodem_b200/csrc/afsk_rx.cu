@@ -455,12 +455,16 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
                 Ns += __shfl_xor_sync(0xFFFFFFFFu, Ns, o);
                 accA += __shfl_xor_sync(0xFFFFFFFFu, accA, o);
             }
-            // 2 * sum|T - amp| = 65535 * (bf - U) + (U + 2 * Xn)      (mark_diff < space_diff :346-351)
-            const int M2 = 65535 * (bf - Um) + Um + 2 * Nm;
-            const int S2 = 65535 * (bf - Us) + Us + 2 * Ns;
-            const int dlt = S2 - M2;
-            bool b1 = dlt >= two_bf;
-            if (dlt > 0 && dlt < two_bf) b1 = M2 < (S2 / two_bf) * two_bf;   // floor(M/bf) < floor(S/bf)
+            // 2 * sum|T - amp| = 65535 * bf - 65534 * U + 2 * Xn       (mark_diff < space_diff :346-351)
+            // so 2 * (S - M) = 65534 * (Um - Us) + 2 * (Ns - Nm) with |Ns - Nm| <= bf: the sign of
+            // Um - Us decides unless the correlations tie, and only then is the floor compared.
+            const int du = Um - Us;
+            bool b1 = du > 0;
+            if (du == 0 && Ns > Nm) {
+                const int M2 = 65535 * bf - 65534 * Um + 2 * Nm;
+                const int S2 = M2 + 2 * (Ns - Nm);
+                b1 = (S2 - M2 >= two_bf) || (M2 < (S2 / two_bf) * two_bf);   // floor(M/bf) < floor(S/bf)
+            }
             const bool valid = (part == 0) && (w < m.nwin);
             bit = valid && b1;
             quiet = valid && (accA < m.thr_bf);                // getAmplitude(chunk) < amp_end :375
@@ -509,8 +513,8 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
 }
 
 // ------------------------------------------------------------------------------ k_frame ----
-template <int kThreads>
-__device__ __forceinline__ long long block_min_ll(long long v, long long *scratch)
+template <int kThreads, typename T>
+__device__ __forceinline__ T block_min(T v, T *scratch)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -518,7 +522,7 @@ __device__ __forceinline__ long long block_min_ll(long long v, long long *scratc
     __syncthreads();                       // scratch reuse
     if (lane == 0) scratch[warp] = v;
     __syncthreads();
-    long long r = scratch[0];
+    T r = scratch[0];
 #pragma unroll
     for (int w = 1; w < kThreads / 32; w++) r = min(r, scratch[w]);
     return r;
@@ -535,78 +539,106 @@ __device__ __forceinline__ uint32_t hamming74_nibble(uint32_t cw)
     return (((cw >> 2) & 1u) << 3) | (((cw >> 4) & 1u) << 2) | (((cw >> 5) & 1u) << 1) | ((cw >> 6) & 1u);
 }
 
+// two 7-bit codewords (14 bits, first received in bit 0) -> one byte, first nibble high (:393-399);
+// lut[cw] = corrected nibble of codeword cw (128 entries, built per CTA)
+__device__ __forceinline__ uint32_t decode_byte(uint32_t v14, const uint8_t *lut)
+{
+    return ((uint32_t)lut[v14 & 0x7Fu] << 4) | (uint32_t)lut[(v14 >> 7) & 0x7Fu];
+}
+
 // kThreads x kWords plane words are searched per block step: <128,4> for ordinary captures,
 // <512,8> when a capture has more than 16384 windows (e.g. 64 KB payloads at 300 baud).
-template <int kThreads, int kWords>
+// idx_t = int unless a capture has 2^30 or more windows.
+template <int kThreads, int kWords, typename idx_t>
 __global__ void __launch_bounds__(kThreads) k_frame(const CapDesc *__restrict__ caps,
-                                                         const int32_t *__restrict__ clock,
-                                                         const uint2 *__restrict__ planes,
-                                                         uint8_t *__restrict__ out,
-                                                         AfskRxResult *__restrict__ res)
+                                                    const int32_t *__restrict__ clock,
+                                                    const uint2 *__restrict__ planes,
+                                                    uint8_t *__restrict__ out,
+                                                    AfskRxResult *__restrict__ res)
 {
     const int c = blockIdx.x, tid = threadIdx.x;
     const CapDesc d = caps[c];
     if (d.status0 != 0) return;
-    __shared__ long long scratch[kThreads / 32];
+    __shared__ idx_t scratch[kThreads / 32];
+    __shared__ uint8_t lut[128];
+    if (tid < 128) lut[tid] = (uint8_t)hamming74_nibble((uint32_t)tid);   // visible after the first block_min
     const int clk = clock[c];
-    const long long K = num_windows(d.n, d.bf, clk);
-    const long long nwords = (K + 31) >> 5;
+    const idx_t K = (idx_t)num_windows(d.n, d.bf, clk);
+    const idx_t nwords = (K + 31) >> 5;
     const uint2 *PL = planes + d.plane_base;
-    const long long NONE = 0x7FFFFFFFFFFFFFFFLL;
+    const idx_t NONE = sizeof(idx_t) == 4 ? (idx_t)0x7FFFFFFF : (idx_t)0x7FFFFFFFFFFFFFFFLL;
 
     // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
-    long long kterm = NONE;
-    for (long long base = 0; base < nwords; base += kThreads * kWords) {
-        long long cand = NONE;
+    idx_t kterm = NONE;
+    for (idx_t base = 0; base < nwords; base += kThreads * kWords) {
+        idx_t cand = NONE;
 #pragma unroll
         for (int r = kWords - 1; r >= 0; r--) {
-            const long long j = base + tid + r * kThreads;
+            const idx_t j = base + tid + r * kThreads;
             if (j < nwords) {
-                const uint64_t v = ((uint64_t)PL[j].x << 32) | (j ? PL[j - 1].x : 0u);
-                uint32_t M = (uint32_t)((v >> 29) & ~(v >> 30) & ~(v >> 31) & ~(v >> 32));
-                const long long rem = K - 32 * j;
+                const uint32_t cur = PL[j].x, prev = j ? PL[j - 1].x : 0u;
+                // bit t of M: b[k-3] & ~b[k-2] & ~b[k-1] & ~b[k] for k = 32j + t
+                uint32_t M = __funnelshift_l(prev, cur, 3) & ~__funnelshift_l(prev, cur, 2) &
+                             ~__funnelshift_l(prev, cur, 1) & ~cur;
+                const idx_t rem = K - 32 * j;
                 if (rem < 32) M &= (1u << rem) - 1u;
                 if (M) cand = 32 * j + (__ffs(M) - 1);
             }
         }
-        kterm = block_min_ll<kThreads>(cand, scratch);
+        kterm = block_min<kThreads, idx_t>(cand, scratch);
         if (kterm != NONE) break;
     }
-    const long long k0 = (kterm == NONE) ? K : kterm + 1;
+    __syncthreads();                                 // lut (nwords may be 0: no block_min ran)
+    const idx_t k0 = (kterm == NONE) ? K : kterm + 1;
     // phase 2 (:372-378): first quiet window at or after k0
-    long long k1 = NONE;
-    for (long long base = k0 >> 5; base < nwords; base += kThreads * kWords) {
-        long long cand = NONE;
+    idx_t k1 = NONE;
+    for (idx_t base = k0 >> 5; base < nwords; base += kThreads * kWords) {
+        idx_t cand = NONE;
 #pragma unroll
         for (int r = kWords - 1; r >= 0; r--) {
-            const long long j = base + tid + r * kThreads;
+            const idx_t j = base + tid + r * kThreads;
             if (j < nwords) {
                 uint32_t M = PL[j].y;
                 if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
-                const long long rem = K - 32 * j;
+                const idx_t rem = K - 32 * j;
                 if (rem < 32) M &= (1u << rem) - 1u;
                 if (M) cand = 32 * j + (__ffs(M) - 1);
             }
         }
-        k1 = block_min_ll<kThreads>(cand, scratch);
+        k1 = block_min<kThreads, idx_t>(cand, scratch);
         if (k1 != NONE) break;
     }
     if (k1 == NONE) k1 = K;
-    const long long nbits = k1 - k0;
-    const long long nbytes = (nbits / 7) / 2;        // ECC.decode :156, __bitsToBytes :396
-    uint8_t *o = out + d.out_off;
-#pragma unroll 4
-    for (long long i = tid; i < nbytes; i += kThreads) {
-        const long long pos = k0 + 14 * i;
+    const idx_t nbits = k1 - k0;
+    const idx_t nbytes = (nbits / 7) / 2;            // ECC.decode :156, __bitsToBytes :396
+    uint8_t *o = out + d.out_off;                    // 16-byte aligned
+    // four bytes (56 coded bits) per thread step: three plane words, one 32-bit store
+    const idx_t nquad = nbytes >> 2;
+    for (idx_t i = tid; i < nquad; i += kThreads) {
+        const idx_t pos = k0 + 56 * i;
+        const idx_t wi = pos >> 5;
+        const uint32_t sh = (uint32_t)(pos & 31);
+        const uint32_t w0 = PL[wi].x, w1 = PL[wi + 1].x, w2 = PL[wi + 2].x;
+        uint32_t word = 0;
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++) {
+            const uint32_t sft = sh + 14u * jb;                 // 0 .. 73
+            const uint32_t a = sft < 32 ? w0 : (sft < 64 ? w1 : w2);
+            const uint32_t bb = sft < 32 ? w1 : (sft < 64 ? w2 : 0u);
+            word |= decode_byte(__funnelshift_r(a, bb, sft & 31u) & 0x3FFFu, lut) << (8 * jb);
+        }
+        reinterpret_cast<uint32_t *>(o)[i] = word;
+    }
+    for (idx_t i = 4 * nquad + tid; i < nbytes; i += kThreads) {
+        const idx_t pos = k0 + 14 * i;
         const uint32_t lo = PL[pos >> 5].x, hi = PL[(pos >> 5) + 1].x;
-        const uint32_t val = __funnelshift_r(lo, hi, (uint32_t)(pos & 31));
-        o[i] = (uint8_t)((hamming74_nibble(val & 0x7Fu) << 4) | hamming74_nibble((val >> 7) & 0x7Fu));
+        o[i] = (uint8_t)decode_byte(__funnelshift_r(lo, hi, (uint32_t)(pos & 31)) & 0x3FFFu, lut);
     }
     if (tid == 0) {
         AfskRxResult r;
         r.status = nbits > 0 ? AFSK_ST_OK : AFSK_ST_NO_DATA;
         r.clock = clk;
-        r.train_end = (long long)clk + k0 * d.bf;     // "Training sequence terminated on frame" :368
+        r.train_end = (long long)clk + (long long)k0 * d.bf;   // "Training sequence terminated on frame" :368
         r.nbits = nbits;
         r.nbytes = nbits > 0 ? nbytes : 0;
         res[c] = r;
@@ -655,7 +687,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__re
     for (long long base = 1; base <= last; base += kFrameThreads) {
         const long long j = base + tid;
         long long cand = (j <= last && A[j] > amp_start) ? j : NONE;     // :306
-        open = block_min_ll<kFrameThreads>(cand, scratch);
+        open = block_min<kFrameThreads, long long>(cand, scratch);
         if (open != NONE) break;
     }
     long long close = NONE;
@@ -663,7 +695,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__re
         for (long long base = open + 1; base < nch; base += kFrameThreads) {
             const long long j = base + tid;
             long long cand = (j < nch && A[j] < amp_end) ? j : NONE;     // :316
-            close = block_min_ll<kFrameThreads>(cand, scratch);
+            close = block_min<kFrameThreads, long long>(cand, scratch);
             if (close != NONE) break;
         }
     }
@@ -824,8 +856,8 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
             if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
             g.caps.push_back(c);
             g.tile_first.push_back(g.tile_first.back() + (int32_t)ntiles);
-            words += ntiles * (g.wt / 32) + 2;
-            cap_bytes = kmax / 14 + 16;
+            words += ntiles * (g.wt / 32) + 4;
+            cap_bytes = (kmax / 14 + 16 + 15) & ~(int64_t)15;
         }
         P->out_off[c + 1] = P->out_off[c] + cap_bytes;
     }
@@ -922,6 +954,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
 {
     if (!P || (P->B > 0 && (!d_samples || !d_out || !d_res))) { afsk_set_error("afsk_rx_decode: null argument"); return AFSK_E_ARG; }
     if ((reinterpret_cast<uintptr_t>(d_samples) & 15) != 0) { afsk_set_error("afsk_rx_decode: d_samples must be 16-byte aligned"); return AFSK_E_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_out) & 3) != 0) { afsk_set_error("afsk_rx_decode: d_out must be 4-byte aligned"); return AFSK_E_ARG; }
     if (P->B == 0) return AFSK_OK;
     AfskDeviceGuard guard(P->device);
     if (!guard.ok) { afsk_set_error("cannot select device %d", P->device); return AFSK_E_CUDA; }
@@ -944,10 +977,12 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
             P->timing_events.emplace_back(e0, e1);
         }
     }
-    if (P->max_windows > 16384)
-        k_frame<512, 8><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
+    if (P->max_windows >= ((int64_t)1 << 30))
+        k_frame<512, 8, long long><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
+    else if (P->max_windows > 16384)
+        k_frame<512, 8, int><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     else
-        k_frame<128, 4><<<P->B, 128, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
+        k_frame<128, 4, int><<<P->B, 128, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     AFSK_CUDA(cudaGetLastError());
     return AFSK_OK;
 }

@@ -49,8 +49,16 @@ __device__ __forceinline__ uint32_t tx_bit(long long b, const TxDesc &d, const u
     const long long t = b - d.ts_bits;
     if (t < 4) return t == 0 ? 1u : 0u;                      // terminator mark, space x3     :460-462
     const long long j = t - 4;                               // coded bit index
-    const long long g = j / 7;                               // nibble index, high nibble first :446-450
-    const uint32_t r = (uint32_t)(j - 7 * g);
+    long long g;                                             // nibble index, high nibble first :446-450
+    uint32_t r;
+    if (j < 0x7FFFFFFFLL) {                                  // 32-bit divide for all but > 150 MB payloads
+        const uint32_t g32 = (uint32_t)j / 7u;
+        r = (uint32_t)j - 7u * g32;
+        g = g32;
+    } else {
+        g = j / 7;
+        r = (uint32_t)(j - 7 * g);
+    }
     const uint32_t byte = pay[d.pay_off + (g >> 1)];
     const uint32_t nib = (g & 1) ? (byte & 15u) : (byte >> 4);
     return (hamming74_encode(nib) >> r) & 1u;

@@ -268,6 +268,66 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t x)
 
 constexpr int kFlushVecs = 15;      // 120 samples: keeps |T.c| <= 127 inside one packed accumulator
 
+// Producer (one lane): walks the tile range [lo, hi) of this CTA, resolves tile -> capture with an
+// incremental walk over the group's tile prefix, and feeds the shared-memory ring: tile metadata,
+// mbarrier expect_tx, one 1-D TMA bulk copy per tile.
+__device__ __forceinline__ void demod_produce(const DemodParams &p, int lo, int hi, uint8_t *stage_base,
+                                              TileMeta *meta, uint64_t *full, uint64_t *empty)
+{
+    const int S = p.stages;
+    int a = 0, b = p.ng;
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (p.gtile_first[mid] <= lo) a = mid; else b = mid;
+    }
+    int ci = a, this_first = p.gtile_first[ci], next_first = p.gtile_first[ci + 1];
+    bool have = false;
+    CapDesc d;
+    long long K = 0;
+    int clk = 0;
+    int s = 0;
+    uint32_t ph = 0;                                       // parity of the use count of stage s
+    for (int it = lo; it < hi; ++it) {
+        while (it >= next_first) {
+            ci++;
+            this_first = next_first;
+            next_first = p.gtile_first[ci + 1];
+            have = false;
+        }
+        if (!have) {
+            const int c = p.gcaps[ci];
+            d = p.caps[c];
+            clk = p.clock[c];
+            K = num_windows(d.n, p.bf, clk);
+            have = true;
+        }
+        const long long k0t = (long long)(it - this_first) * p.wt;
+        long long nw = K - k0t;
+        const int nwin = nw <= 0 ? 0 : (nw > p.wt ? p.wt : (int)nw);
+        const long long g0 = d.off + clk + k0t * p.bf;          // first sample of the tile
+        const long long ga = g0 & ~7LL;
+        if (it - lo >= S) {
+            while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(256);
+        }
+        TileMeta m;
+        m.e0 = (int)(g0 - ga);
+        m.nwin = nwin;
+        m.thr_bf = d.thr * p.bf;
+        m.pad = 0;
+        m.word_base = d.plane_base + (k0t >> 5);
+        m.pad2 = 0;
+        meta[s] = m;
+        if (nwin > 0) {
+            const uint32_t bytes = (uint32_t)((((long long)m.e0 + (long long)nwin * p.bf) * 2 + 15) & ~15LL);
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_g2s(stage_base + (size_t)s * p.stage_bytes, p.samples + ga, bytes, &full[s]);
+        } else {
+            mbar_arrive(&full[s]);
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+    }
+}
+
 // kNT > 0: the number of vector steps per thread is a compile-time constant (fully unrolled, one
 // packed accumulator); kNT == 0: run-time count with a flush every kFlushVecs vectors.
 // kMerge: the thread segment is a multiple of 8 samples, so the partial head vector (slots >= e)
@@ -339,59 +399,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     if (lo >= hi) return;
 
     if (warp == kConsumerThreads / 32) {
-        // ------------------------------------------------------------ producer warp ----
-        if (lane != 0) return;
-        int a = 0, b = p.ng;
-        while (b - a > 1) {
-            const int mid = (a + b) >> 1;
-            if (p.gtile_first[mid] <= lo) a = mid; else b = mid;
-        }
-        int ci = a, this_first = p.gtile_first[ci], next_first = p.gtile_first[ci + 1];
-        bool have = false;
-        CapDesc d;
-        long long K = 0;
-        int clk = 0;
-        int s = 0;
-        uint32_t ph = 0;                                       // parity of the use count of stage s
-        for (int it = lo; it < hi; ++it) {
-            while (it >= next_first) {
-                ci++;
-                this_first = next_first;
-                next_first = p.gtile_first[ci + 1];
-                have = false;
-            }
-            if (!have) {
-                const int c = p.gcaps[ci];
-                d = p.caps[c];
-                clk = p.clock[c];
-                K = num_windows(d.n, p.bf, clk);
-                have = true;
-            }
-            const long long k0t = (long long)(it - this_first) * p.wt;
-            long long nw = K - k0t;
-            const int nwin = nw <= 0 ? 0 : (nw > p.wt ? p.wt : (int)nw);
-            const long long g0 = d.off + clk + k0t * p.bf;          // first sample of the tile
-            const long long ga = g0 & ~7LL;
-            if (it - lo >= S) {
-                while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(256);
-            }
-            TileMeta m;
-            m.e0 = (int)(g0 - ga);
-            m.nwin = nwin;
-            m.thr_bf = d.thr * p.bf;
-            m.pad = 0;
-            m.word_base = d.plane_base + (k0t >> 5);
-            m.pad2 = 0;
-            meta[s] = m;
-            if (nwin > 0) {
-                const uint32_t bytes = (uint32_t)((((long long)m.e0 + (long long)nwin * p.bf) * 2 + 15) & ~15LL);
-                mbar_arrive_expect_tx(&full[s], bytes);
-                bulk_g2s(stage_base + (size_t)s * p.stage_bytes, p.samples + ga, bytes, &full[s]);
-            } else {
-                mbar_arrive(&full[s]);
-            }
-            if (++s == S) { s = 0; ph ^= 1u; }
-        }
+        if (lane == 0) demod_produce(p, lo, hi, stage_base, meta, full, empty);
         return;
     }
 
@@ -507,6 +515,146 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
                     if (lane == 0 && warp * 32 < m.nwin) p.planes[m.word_base + warp] = make_uint2(bw, qw);
                 }
             }
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+    }
+}
+
+// ------------------------------------------------------------------------ k_demod_small ----
+// Short windows (bf = 8, 16, 24: 6000 / 3000 / 2000 baud): one thread decodes kWpt consecutive
+// windows of kM vectors each, so the per-tile bookkeeping is paid once per 48-64 samples instead of
+// once per 8-24.  Every vector is re-aligned to the window grid with 4 PRMTs (slots >= e from
+// vector i, slots < e from vector i+1), the +/-1 weights are uniform over the tile (alignment e is
+// per tile) and live in registers, and threads visit their windows in a lane-rotated order so that
+// the 128-bit shared-memory loads of a warp fall in different banks.
+__device__ __forceinline__ void accum4_full(uint32_t w0, uint32_t w1, uint32_t mw, uint32_t sw, uint32_t k512,
+                                            int &accM, int &accS, int &accA)
+{
+    const uint32_t g0 = __viaddmin_u16x2(w0, k512, 0x04010401u);
+    const uint32_t g1 = __viaddmin_u16x2(w1, k512, 0x04010401u);
+    const uint32_t t0 = g0 + 0x7BFF7BFFu;
+    const uint32_t t1 = g1 + 0x7BFF7BFFu;
+    const uint32_t s4 = prmt(w0, w1, 0xFDB9u);
+    const uint32_t nz4 = prmt(t0, t1, 0xFDB9u);
+    const uint32_t sg4 = s4 | 0x01010101u;
+    const uint32_t v4 = nz4 & sg4;
+    accM = dp4a_us(v4, mw, accM);
+    accS = dp4a_us(v4, sw, accS);
+    accA = __dp2a_lo((int)w0, (int)sg4, accA);
+    accA = __dp2a_hi((int)w1, (int)sg4, accA);
+}
+
+template <int kM, int kWpt>
+__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.stages;
+    uint8_t *stage_base = smem;
+    uint4 *wtab = reinterpret_cast<uint4 *>(smem + (size_t)S * p.stage_bytes);     // [8 alignments][kM + 1]
+    TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + 8 * (kM + 1));
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
+    uint64_t *empty = full + kMaxStages;
+    constexpr int kBf = 8 * kM, kSeg = kBf * kWpt, kLanesPerWord = 32 / kWpt;
+
+    // weights of re-aligned vector i at alignment e: slot s holds window sample 8i + ((s - e) mod 8);
+    // entry kM holds the 4 PRMT selectors
+    if (tid < 8 * (kM + 1)) {
+        const int e = tid / (kM + 1), i = tid % (kM + 1);
+        if (i < kM) {
+            const int q = kBf >> 2;
+            uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u};
+#pragma unroll
+            for (int sl = 0; sl < 8; sl++) {
+                const int r = 8 * i + ((sl - e + 8) & 7), qd = r / q, sh = 8 * (sl & 3);
+                mk[sl >> 2] |= ((qd & 1) ? 0xFFu : 0x01u) << sh;
+                sp[sl >> 2] |= ((qd & 2) ? 0xFFu : 0x01u) << sh;
+            }
+            wtab[tid] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
+        } else {
+            uint32_t sel[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) sel[j] = (2 * j >= e) ? 0x3210u : ((2 * j + 1 < e) ? 0x7654u : 0x3254u);
+            wtab[tid] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int per = (p.total_items + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per;
+    const int hi = min(p.total_items, lo + per);
+    if (lo >= hi) return;
+    if (warp == kConsumerThreads / 32) {
+        if (lane == 0) demod_produce(p, lo, hi, stage_base, meta, full, empty);
+        return;
+    }
+
+    const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int n = 0; n < hi - lo; ++n) {
+        mbar_wait(&full[s], ph);
+        const TileMeta m = meta[s];
+        uint32_t bits = 0, quiet = 0;
+        if (m.nwin > 0) {
+            const uint4 *wt = wtab + m.e0 * (kM + 1);
+            uint4 W[kM];
+#pragma unroll
+            for (int i = 0; i < kM; i++) W[i] = wt[i];
+            const uint4 sel = wt[kM];
+            // e0 < 8 and kSeg % 8 == 0: the thread's first vector is tid * kSeg / 8
+            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + tid * (kSeg / 8);
+#pragma unroll
+            for (int j = 0; j < kWpt; j++) {
+                const int jj = (j + tid) & (kWpt - 1);           // lane-rotated window order
+                int accM = 0, accS = 0, accA = 0;
+                uint4 cur = dp[jj * kM];
+#pragma unroll
+                for (int i = 0; i < kM; i++) {
+                    const uint4 nxt = dp[jj * kM + i + 1];
+                    const uint32_t x0 = prmt(cur.x, nxt.x, sel.x), x1 = prmt(cur.y, nxt.y, sel.y);
+                    const uint32_t x2 = prmt(cur.z, nxt.z, sel.z), x3 = prmt(cur.w, nxt.w, sel.w);
+                    accum4_full(x0, x1, W[i].x, W[i].z, k512, accM, accS, accA);
+                    accum4_full(x2, x3, W[i].y, W[i].w, k512, accM, accS, accA);
+                    cur = nxt;
+                }
+                // acc = 256 * T.n + T.c with |T.c| <= 24: decide as in k_demod
+                const int Um = (int)((unsigned)accM << 24) >> 24, Us = (int)((unsigned)accS << 24) >> 24;
+                const int du = Um - Us;
+                bool b1 = du > 0;
+                if (du == 0) {
+                    const int Nm = (accM - Um) >> 8, Ns = (accS - Us) >> 8;
+                    if (Ns > Nm) {
+                        const int M2 = 65535 * kBf - 65534 * Um + 2 * Nm;
+                        const int S2 = M2 + 2 * (Ns - Nm);
+                        b1 = (S2 - M2 >= 2 * kBf) || (M2 < (S2 / (2 * kBf)) * (2 * kBf));
+                    }
+                }
+                const bool valid = tid * kWpt + jj < m.nwin;
+                bits |= (uint32_t)(valid && b1) << jj;
+                quiet |= (uint32_t)(valid && (accA < m.thr_bf)) << jj;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (m.nwin > 0) {
+            // kLanesPerWord threads hold the kWpt-bit pieces of one plane word
+            uint32_t bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
+            uint32_t qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
+#pragma unroll
+            for (int o = 1; o < kLanesPerWord; o <<= 1) {
+                bw |= __shfl_xor_sync(0xFFFFFFFFu, bw, o);
+                qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
+            }
+            const int word = (tid * kWpt) >> 5;
+            if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin) p.planes[m.word_base + word] = make_uint2(bw, qw);
         }
         if (++s == S) { s = 0; ph ^= 1u; }
     }
@@ -712,6 +860,7 @@ __global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__re
 
 struct Group {
     int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, stage_bytes = 0, stages = 0;
+    int small_wpt = 0;            // > 0: k_demod_small<bf/8, small_wpt>
     size_t smem = 0;
     int grid = 0;
     std::vector<int32_t> caps, tile_first;
@@ -727,7 +876,9 @@ struct Group {
 
 static cudaError_t demod_set_smem_attr()
 {
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_demod_small<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 #define X(NT, MG) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod<NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     AFSK_DEMOD_VARIANTS(X)
@@ -764,6 +915,9 @@ struct AfskRxPlan {
 
 static size_t demod_smem_bytes(const Group &g)
 {
+    if (g.small_wpt)
+        return (size_t)g.stages * g.stage_bytes + (size_t)8 * (g.bf / 8 + 1) * 16 + kMaxStages * sizeof(TileMeta) +
+               2 * kMaxStages * sizeof(uint64_t);
     return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * (8 * (2 * g.nt + 1) + 1) * 16 +
            kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t) + 2 * kConsumerThreads;
 }
@@ -772,6 +926,19 @@ static bool configure_group(Group &g, int bf)
 {
     g.bf = bf;
     g.tpw_log2 = 0;
+    if (bf == 8 || bf == 16 || bf == 24) {
+        // short windows: several windows per thread (k_demod_small)
+        g.small_wpt = bf == 8 ? 8 : (bf == 16 ? 4 : 2);
+        g.seg = bf * g.small_wpt;
+        g.nv = g.seg / 8 + 1;
+        g.nt = g.nv; g.merge = 0;
+        g.wt = kConsumerThreads * g.small_wpt;
+        g.stage_bytes = ((g.wt * bf * 2 + 16 + 128) + 127) & ~127;
+        const size_t budget_s = 100 * 1024;
+        g.stages = (int)std::min<size_t>(4, std::max<size_t>(1, budget_s / g.stage_bytes));
+        g.smem = demod_smem_bytes(g);
+        return true;
+    }
     while ((bf >> g.tpw_log2) > 48 && g.tpw_log2 < 3) g.tpw_log2++;
     const int tpw = 1 << g.tpw_log2;
     g.seg = (bf + tpw - 1) / tpw;
@@ -971,7 +1138,10 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);
+        if (g.small_wpt == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt == 4) k_demod_small<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt == 2) k_demod_small<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);
         if (e0 && e1) {
             cudaEventRecord(e1, st);
             P->timing_events.emplace_back(e0, e1);

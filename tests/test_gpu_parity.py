@@ -128,7 +128,7 @@ def test_tx_batch_matches_oracle_mixed():
     s.close()
 
 
-@pytest.mark.parametrize("baud", [300, 600, 800, 1200, 2400, 4000, 6000, 12000, 100, 24, 375, 1000])
+@pytest.mark.parametrize("baud", [300, 600, 800, 1200, 2400, 4000, 6000, 12000, 100, 24, 375, 1000, 2000, 3000, 1500, 500])
 def test_random_sweep_vs_oracle(baud):
     """Seeded impairments per baud: lead silence (arbitrary alignment), gain, AWGN, truncation,
     thresholds — final bytes AND the four stage integers must equal the oracle's."""

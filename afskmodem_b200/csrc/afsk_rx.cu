@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     }
     // y = up to 4104 samples starting at the 16-byte boundary at or below the capture start.
     // Qs[4 + i] = y[0] + ... + y[i] (mod 2^32), Qs[3] = 0, so P[i] = sum y[0..i) = Qs[3 + i].
-    __shared__ __align__(16) uint32_t Qs[4 + AFSK_SYNC_FRAMES + 8];
+    __shared__ __align__(16) uint32_t Qs[4 + AFSK_SYNC_FRAMES + 8 + kClockThreads];
     __shared__ uint32_t warp_tot[kClockThreads / 32];
     __shared__ uint32_t warp_min[kClockThreads / 32];
     const uint32_t *P = Qs + 3;
@@ -167,15 +167,20 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     constexpr int kPerThread = AFSK_SYNC_FRAMES / kClockThreads;   // 32 candidates per thread at most
     uint32_t Dv[kPerThread];
     uint32_t best = 0xFFFFFFFFu;
+    // seven prefix taps per candidate, candidate i = tid + 128 k (conflict-free: consecutive lanes,
+    // consecutive words); the last partial round reads up to 127 words past the scanned range
+    // (inside Qs, values unused)
+    const uint32_t *p0 = P + tid + e, *p1 = p0 + q, *p2 = p0 + 2 * q, *p3 = p0 + 3 * q, *p4 = p0 + bf,
+                   *p5 = p0 + bf + h, *p6 = p0 + 2 * bf;
+    const int kmax = (span + kClockThreads - 1) / kClockThreads;
 #pragma unroll
     for (int k = 0; k < kPerThread; k++) {
-        const int i = tid + k * kClockThreads;
         uint32_t D = 0xFFFFFFFFu;
-        if (i < span) {
-            const int b = i + e;
+        if (k < kmax) {
+            const int o = k * kClockThreads;
             // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO)
-            D = c0 + P[b] - 2u * P[b + q] + 2u * P[b + 2 * q] - 2u * P[b + 3 * q] + 2u * P[b + bf] -
-                2u * P[b + bf + h] + P[b + 2 * bf];
+            D = c0 + p0[o] + p6[o] - 2u * (p1[o] - p2[o] + p3[o] - p4[o] + p5[o]);
+            D = (tid + o < span) ? D : 0xFFFFFFFFu;
         }
         Dv[k] = D;
         best = min(best, D);
@@ -695,7 +700,7 @@ __device__ __forceinline__ uint32_t decode_byte(uint32_t v14, const uint8_t *lut
 }
 
 // kThreads x kWords plane words are searched per block step: <128,4> for ordinary captures,
-// <512,8> when a capture has more than 16384 windows (e.g. 64 KB payloads at 300 baud).
+// <512,8> when a capture has more than 65536 windows (e.g. 64 KB payloads at 300 baud).
 // idx_t = int unless a capture has 2^30 or more windows.
 template <int kThreads, int kWords, typename idx_t>
 __global__ void __launch_bounds__(kThreads) k_frame(const CapDesc *__restrict__ caps,
@@ -1149,7 +1154,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     }
     if (P->max_windows >= ((int64_t)1 << 30))
         k_frame<512, 8, long long><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
-    else if (P->max_windows > 16384)
+    else if (P->max_windows > 65536)
         k_frame<512, 8, int><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     else
         k_frame<128, 4, int><<<P->B, 128, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);

@@ -16,6 +16,7 @@
 //             ECC.decode (:154-163) and __bitsToBytes (:393-399) on the packed bit planes.
 //
 // All arithmetic is integer and bit-exact with the reference (see DESIGN.md for the algebra).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -46,7 +47,7 @@ struct __align__(16) CapDesc {
 };
 
 struct __align__(16) TileMeta {
-    int32_t e0;          // first window's sample offset inside the 16-byte aligned copy
+    int32_t e0;          // first window's sample offset inside the copy (< 64; the copy starts 16-byte aligned)
     int32_t nwin;        // valid windows in this tile (0 -> nothing to do)
     int32_t thr_bf;      // amp_end * bf : quiet <=> sum|x| < thr_bf
     int32_t pad;
@@ -60,6 +61,7 @@ struct DemodParams {
     const int32_t *clock;
     const int32_t *gcaps;        // capture ids of this group, ascending
     const int32_t *gtile_first;  // [ng + 1] prefix of tile counts over gcaps
+    const int32_t *tile_gpos;    // [total_items] tile -> position of its capture in gcaps
     uint2 *planes;               // {bit word, quiet word} per 32 windows
     int ng;
     int total_items;
@@ -254,6 +256,48 @@ __device__ __forceinline__ void unpack_acc(int acc, int &U, int &Xn)
     Xn += (acc - u) >> 8;
 }
 
+// accum4 with every slot inside the window
+__device__ __forceinline__ void accum4_full(uint32_t w0, uint32_t w1, uint32_t mw, uint32_t sw, uint32_t k512,
+                                            int &accM, int &accS, int &accA)
+{
+    const uint32_t g0 = __viaddmin_u16x2(w0, k512, 0x04010401u);
+    const uint32_t g1 = __viaddmin_u16x2(w1, k512, 0x04010401u);
+    const uint32_t t0 = g0 + 0x7BFF7BFFu;
+    const uint32_t t1 = g1 + 0x7BFF7BFFu;
+    const uint32_t s4 = prmt(w0, w1, 0xFDB9u);
+    const uint32_t nz4 = prmt(t0, t1, 0xFDB9u);
+    const uint32_t sg4 = s4 | 0x01010101u;
+    const uint32_t v4 = nz4 & sg4;
+    accM = dp4a_us(v4, mw, accM);
+    accS = dp4a_us(v4, sw, accS);
+    accA = __dp2a_lo((int)w0, (int)sg4, accA);
+    accA = __dp2a_hi((int)w1, (int)sg4, accA);
+}
+
+// Fast path of the merge-mode kernel.  mark - space = 2 D with D = (0, -1, +1, 0) per quarter, so
+//     acc += dp4a.u32.s32(v4, D4)   = 256 * D.n + D.c ,   D.c = (Um - Us) / 2 ,  D.n = (Nm - Ns) / 2
+// decides the bit whenever Um != Us or Ns <= Nm (see the decision below); one IDP.4A instead of two.
+__device__ __forceinline__ void accum4_d(uint32_t w0, uint32_t w1, uint32_t dw, uint32_t k512, int &accD, int &accA)
+{
+    const uint32_t g0 = __viaddmin_u16x2(w0, k512, 0x04010401u);
+    const uint32_t g1 = __viaddmin_u16x2(w1, k512, 0x04010401u);
+    const uint32_t t0 = g0 + 0x7BFF7BFFu;
+    const uint32_t t1 = g1 + 0x7BFF7BFFu;
+    const uint32_t s4 = prmt(w0, w1, 0xFDB9u);
+    const uint32_t nz4 = prmt(t0, t1, 0xFDB9u);
+    const uint32_t sg4 = s4 | 0x01010101u;
+    accD = dp4a_us(nz4 & sg4, dw, accD);
+    accA = __dp2a_lo((int)w0, (int)sg4, accA);
+    accA = __dp2a_hi((int)w1, (int)sg4, accA);
+}
+// amplitude only: four samples whose D weights are all zero
+__device__ __forceinline__ void accum4_a(uint32_t w0, uint32_t w1, int &accA)
+{
+    const uint32_t sg4 = prmt(w0, w1, 0xFDB9u) | 0x01010101u;
+    accA = __dp2a_lo((int)w0, (int)sg4, accA);
+    accA = __dp2a_hi((int)w1, (int)sg4, accA);
+}
+
 // keep every 2nd / 4th bit of a ballot, packed to the low 16 / 8 bits
 __device__ __forceinline__ uint32_t squeeze2(uint32_t x)
 {
@@ -273,63 +317,81 @@ __device__ __forceinline__ uint32_t squeeze4(uint32_t x)
 
 constexpr int kFlushVecs = 15;      // 120 samples: keeps |T.c| <= 127 inside one packed accumulator
 
-// Producer (one lane): walks the tile range [lo, hi) of this CTA, resolves tile -> capture with an
-// incremental walk over the group's tile prefix, and feeds the shared-memory ring: tile metadata,
+// Tiles are dealt round-robin: CTA b handles tiles b, b + G, b + 2G, ... (balanced to one tile; at any
+// moment the whole grid streams one contiguous span of the sample buffer).  The producer WARP prepares tiles 32 at a time: lane j resolves tile
+// n + j (tile -> capture map, capture descriptor, clock index: three dependent global loads) one
+// batch ahead of use, then the lanes take turns feeding the shared-memory ring: tile metadata,
 // mbarrier expect_tx, one 1-D TMA bulk copy per tile.
-__device__ __forceinline__ void demod_produce(const DemodParams &p, int lo, int hi, uint8_t *stage_base,
-                                              TileMeta *meta, uint64_t *full, uint64_t *empty)
+struct TileJob {
+    TileMeta m;
+    long long ga;        // first sample of the bulk copy
+    uint32_t bytes;      // 0: no valid window in the tile
+};
+
+__device__ __forceinline__ TileJob demod_tile_job(const DemodParams &p, int it, long long base_mis)
 {
-    const int S = p.stages;
-    int a = 0, b = p.ng;
-    while (b - a > 1) {
-        const int mid = (a + b) >> 1;
-        if (p.gtile_first[mid] <= lo) a = mid; else b = mid;
-    }
-    int ci = a, this_first = p.gtile_first[ci], next_first = p.gtile_first[ci + 1];
-    bool have = false;
-    CapDesc d;
-    long long K = 0;
-    int clk = 0;
+    TileJob j;
+    const int ci = p.tile_gpos[it];
+    const int c = p.gcaps[ci];
+    const int first = p.gtile_first[ci];
+    const int4 d0 = *reinterpret_cast<const int4 *>(&p.caps[c].off);          // off, n
+    const int4 d1 = *reinterpret_cast<const int4 *>(&p.caps[c].plane_base);   // plane_base, out_off
+    const int thr = p.caps[c].thr;
+    const int clk = p.clock[c];
+    const long long off = ((long long)d0.y << 32) | (unsigned)d0.x, n = ((long long)d0.w << 32) | (unsigned)d0.z;
+    const long long plane_base = ((long long)d1.y << 32) | (unsigned)d1.x;
+    const long long K = num_windows(n, p.bf, clk);
+    const long long k0t = (long long)(it - first) * p.wt;
+    const long long nw = K - k0t;
+    const int nwin = nw <= 0 ? 0 : (nw > p.wt ? p.wt : (int)nw);
+    const long long g0 = off + clk + k0t * p.bf;             // first sample of the tile
+    // copy from the 128-byte line holding that sample (misaligned bulk copies cost ~3.5 % of the
+    // read bandwidth), unless the line starts before the buffer
+    long long ga = ((g0 + base_mis) & ~63LL) - base_mis;
+    if (ga < 0) ga = g0 & ~7LL;
+    j.m.e0 = (int)(g0 - ga);
+    j.m.nwin = nwin;
+    j.m.thr_bf = thr * p.bf;
+    j.m.pad = 0;
+    j.m.word_base = plane_base + (k0t >> 5);
+    j.m.pad2 = 0;
+    j.ga = ga;
+    j.bytes = nwin > 0 ? (uint32_t)((((long long)j.m.e0 + (long long)nwin * p.bf) * 2 + 15) & ~15LL) : 0u;
+    return j;
+}
+
+__device__ __forceinline__ void demod_produce(const DemodParams &p, int ntile, uint8_t *stage_base, TileMeta *meta,
+                                              uint64_t *full, uint64_t *empty)
+{
+    const int S = p.stages, lane = threadIdx.x & 31;
+    const int G = (int)gridDim.x, first_tile = (int)blockIdx.x;
+    const long long base_mis = (long long)((reinterpret_cast<uintptr_t>(p.samples) >> 1) & 63);   // multiple of 8
     int s = 0;
     uint32_t ph = 0;                                       // parity of the use count of stage s
-    for (int it = lo; it < hi; ++it) {
-        while (it >= next_first) {
-            ci++;
-            this_first = next_first;
-            next_first = p.gtile_first[ci + 1];
-            have = false;
+    TileJob next = {};
+    if (lane < ntile) next = demod_tile_job(p, first_tile + lane * G, base_mis);
+    for (int base = 0; base < ntile; base += 32) {
+        const TileJob cur = next;
+        if (base + 32 + lane < ntile) next = demod_tile_job(p, first_tile + (base + 32 + lane) * G, base_mis);
+        const int cnt = min(32, ntile - base);
+        for (int j = 0; j < cnt; j++) {
+            if (lane == j) {
+                if (base + j >= S) {
+                    while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(128);
+                }
+                meta[s] = cur.m;
+                if (cur.bytes) {
+                    mbar_arrive_expect_tx(&full[s], cur.bytes);
+                    bulk_g2s(stage_base + (size_t)s * p.stage_bytes, p.samples + cur.ga, cur.bytes, &full[s]);
+                } else {
+                    mbar_arrive(&full[s]);
+                }
+            }
+            // the lanes must feed the ring in tile order: a lane two uses of a stage ahead would see
+            // the parity it waits for already satisfied by the previous use
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
-        if (!have) {
-            const int c = p.gcaps[ci];
-            d = p.caps[c];
-            clk = p.clock[c];
-            K = num_windows(d.n, p.bf, clk);
-            have = true;
-        }
-        const long long k0t = (long long)(it - this_first) * p.wt;
-        long long nw = K - k0t;
-        const int nwin = nw <= 0 ? 0 : (nw > p.wt ? p.wt : (int)nw);
-        const long long g0 = d.off + clk + k0t * p.bf;          // first sample of the tile
-        const long long ga = g0 & ~7LL;
-        if (it - lo >= S) {
-            while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(256);
-        }
-        TileMeta m;
-        m.e0 = (int)(g0 - ga);
-        m.nwin = nwin;
-        m.thr_bf = d.thr * p.bf;
-        m.pad = 0;
-        m.word_base = d.plane_base + (k0t >> 5);
-        m.pad2 = 0;
-        meta[s] = m;
-        if (nwin > 0) {
-            const uint32_t bytes = (uint32_t)((((long long)m.e0 + (long long)nwin * p.bf) * 2 + 15) & ~15LL);
-            mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(stage_base + (size_t)s * p.stage_bytes, p.samples + ga, bytes, &full[s]);
-        } else {
-            mbar_arrive(&full[s]);
-        }
-        if (++s == S) { s = 0; ph ^= 1u; }
     }
 }
 
@@ -386,6 +448,13 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
             }
             uint4 *ent = wtab + part * PSq + e * ESq + 2 * i;
             ent[0] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
+            if (kMerge) {
+                // every slot is inside the window; keep D = (mark - space) / 2 in place of the masks:
+                // bytes differ (0x01 ^ 0xFF = 0xFE) exactly where D = mark
+                const uint32_t x0 = mk[0] ^ sp[0], x1 = mk[1] ^ sp[1];
+                in[0] = mk[0] & prmt(x0, x0, 0xBA98u);
+                in[1] = mk[1] & prmt(x1, x1, 0xBA98u);
+            }
             ent[1] = make_uint4(in[0], in[1], sel[0], sel[1]);
         }
     }
@@ -398,13 +467,11 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     }
     __syncthreads();
 
-    const int per = (p.total_items + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per;
-    const int hi = min(p.total_items, lo + per);
-    if (lo >= hi) return;
+    const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
+    if (ntile <= 0) return;
 
     if (warp == kConsumerThreads / 32) {
-        if (lane == 0) demod_produce(p, lo, hi, stage_base, meta, full, empty);
+        demod_produce(p, ntile, stage_base, meta, full, empty);
         return;
     }
 
@@ -416,9 +483,13 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     // VIADDMNMX takes one immediate; derive the other constant from a runtime value so that it
     // lives in one register instead of being re-materialised before every use (stages < 65536)
     const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
+    // merge-mode fast path: D weights and head/tail selectors of the current alignment (registers)
+    uint32_t Dw[kNT > 0 ? kNT : 1][2], selA = 0, selB = 0;
+    int cur_al = -1;
+    const bool v0_quarter03 = kMerge && kNT >= 4 && p.tpw_log2 == 0;
     int s = 0;
     uint32_t ph = 0;
-    for (int n = 0; n < hi - lo; ++n) {
+    for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
         bool bit = false, quiet = false;
@@ -427,56 +498,127 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (rel >> 3);
             const uint4 *wp = wtab + part * PSq + (rel & 7) * ESq;
             int Um = 0, Nm = 0, Us = 0, Ns = 0, accA = 0;
-            if (kNT > 0) {
-                int accM = 0, accS = 0;
+            bool b1;
+            if (kMerge) {
+                // ---- fast path: one packed accumulator of D = (mark - space) / 2 ----
+                // bf % 8 == 0 here, so every window of the tile has the alignment m.e0 & 7 and a thread's
+                // weights change only when the capture does: they are cached in registers
+                if ((m.e0 & 7) != cur_al) {
+                    cur_al = m.e0 & 7;
+#pragma unroll
+                    for (int i = 0; i < kNT; i++) {
+                        const uint4 av = wp[2 * i + 1];
+                        Dw[i][0] = av.x; Dw[i][1] = av.y;
+                        if (i == 0) { selA = av.z; selB = av.w; }
+                    }
+                }
+                int accD = 0;
 #pragma unroll
                 for (int i = 0; i < kNT; i++) {
                     uint4 dv = dp[i];
-                    const uint4 wv = wp[2 * i];
-                    const uint4 av = wp[2 * i + 1];
-                    if (kMerge && i == 0) {
+                    if (i == 0) {
                         const uint4 tv = dp[kNT];                  // tail vector: slots below e
-                        dv.x = prmt(dv.x, tv.x, av.z);
-                        dv.y = prmt(dv.y, tv.y, av.z >> 16);
-                        dv.z = prmt(dv.z, tv.z, av.w);
-                        dv.w = prmt(dv.w, tv.w, av.w >> 16);
+                        dv.x = prmt(dv.x, tv.x, selA);
+                        dv.y = prmt(dv.y, tv.y, selA >> 16);
+                        dv.z = prmt(dv.z, tv.z, selB);
+                        dv.w = prmt(dv.w, tv.w, selB >> 16);
                     }
-                    accum4(dv.x, dv.y, wv.x, wv.z, av.x, k512, accM, accS, accA);
-                    accum4(dv.z, dv.w, wv.y, wv.w, av.y, k512, accM, accS, accA);
+                    if (i == 0 && v0_quarter03) {
+                        // one thread per window, quarters of >= 8 samples: the merged vector lies in the
+                        // last and first quarter, where mark and space agree (D == 0)
+                        accum4_a(dv.x, dv.y, accA);
+                        accum4_a(dv.z, dv.w, accA);
+                    } else {
+                        accum4_d(dv.x, dv.y, Dw[i][0], k512, accD, accA);
+                        accum4_d(dv.z, dv.w, Dw[i][1], k512, accD, accA);
+                    }
                 }
-                unpack_acc(accM, Um, Nm);
-                unpack_acc(accS, Us, Ns);
+                int dh = (int)((unsigned)accD << 24) >> 24;          // (Um - Us) / 2
+                int nh = (accD - dh) >> 8;                           // (Nm - Ns) / 2
+                for (int o = 1; o < tpw; o <<= 1) {
+                    dh += __shfl_xor_sync(0xFFFFFFFFu, dh, o);
+                    nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o);
+                    accA += __shfl_xor_sync(0xFFFFFFFFu, accA, o);
+                }
+                // 2 * (S - M) = 65534 * (Um - Us) + 2 * (Ns - Nm) with |Ns - Nm| <= bf: the sign of
+                // Um - Us decides; on a tie S <= M (bit 0) unless Ns > Nm, and only then are the two
+                // floors compared, which needs the full sums (rare: noise-only windows)
+                b1 = dh > 0;
+                if (__any_sync(0xFFFFFFFFu, dh == 0 && nh < 0)) {
+                    int accM = 0, accS = 0, accA2 = 0;
+#pragma unroll
+                    for (int i = 0; i < kNT; i++) {
+                        uint4 dv = dp[i];
+                        const uint4 wv = wp[2 * i];
+                        if (i == 0) {
+                            const uint4 tv = dp[kNT];
+                            dv.x = prmt(dv.x, tv.x, selA);
+                            dv.y = prmt(dv.y, tv.y, selA >> 16);
+                            dv.z = prmt(dv.z, tv.z, selB);
+                            dv.w = prmt(dv.w, tv.w, selB >> 16);
+                        }
+                        accum4_full(dv.x, dv.y, wv.x, wv.z, k512, accM, accS, accA2);
+                        accum4_full(dv.z, dv.w, wv.y, wv.w, k512, accM, accS, accA2);
+                    }
+                    unpack_acc(accM, Um, Nm);
+                    unpack_acc(accS, Us, Ns);
+                    for (int o = 1; o < tpw; o <<= 1) {
+                        Um += __shfl_xor_sync(0xFFFFFFFFu, Um, o);
+                        Nm += __shfl_xor_sync(0xFFFFFFFFu, Nm, o);
+                        Us += __shfl_xor_sync(0xFFFFFFFFu, Us, o);
+                        Ns += __shfl_xor_sync(0xFFFFFFFFu, Ns, o);
+                    }
+                    if (Um == Us && Ns > Nm) {
+                        const int M2 = 65535 * bf - 65534 * Um + 2 * Nm;
+                        const int S2 = M2 + 2 * (Ns - Nm);
+                        b1 = (S2 - M2 >= two_bf) || (M2 < (S2 / two_bf) * two_bf);   // floor(M/bf) < floor(S/bf)
+                    }
+                }
             } else {
-                for (int i0 = 0; i0 < nv; i0 += kFlushVecs) {
-                    const int i1 = min(nv, i0 + kFlushVecs);
+                if (kNT > 0) {
                     int accM = 0, accS = 0;
-                    for (int i = i0; i < i1; i++) {
+#pragma unroll
+                    for (int i = 0; i < kNT; i++) {
                         const uint4 dv = dp[i];
                         const uint4 wv = wp[2 * i];
-                        const uint2 av = *reinterpret_cast<const uint2 *>(wp + 2 * i + 1);
+                        const uint4 av = wp[2 * i + 1];
                         accum4(dv.x, dv.y, wv.x, wv.z, av.x, k512, accM, accS, accA);
                         accum4(dv.z, dv.w, wv.y, wv.w, av.y, k512, accM, accS, accA);
                     }
                     unpack_acc(accM, Um, Nm);
                     unpack_acc(accS, Us, Ns);
+                } else {
+                    for (int i0 = 0; i0 < nv; i0 += kFlushVecs) {
+                        const int i1 = min(nv, i0 + kFlushVecs);
+                        int accM = 0, accS = 0;
+                        for (int i = i0; i < i1; i++) {
+                            const uint4 dv = dp[i];
+                            const uint4 wv = wp[2 * i];
+                            const uint2 av = *reinterpret_cast<const uint2 *>(wp + 2 * i + 1);
+                            accum4(dv.x, dv.y, wv.x, wv.z, av.x, k512, accM, accS, accA);
+                            accum4(dv.z, dv.w, wv.y, wv.w, av.y, k512, accM, accS, accA);
+                        }
+                        unpack_acc(accM, Um, Nm);
+                        unpack_acc(accS, Us, Ns);
+                    }
                 }
-            }
-            for (int o = 1; o < tpw; o <<= 1) {
-                Um += __shfl_xor_sync(0xFFFFFFFFu, Um, o);
-                Nm += __shfl_xor_sync(0xFFFFFFFFu, Nm, o);
-                Us += __shfl_xor_sync(0xFFFFFFFFu, Us, o);
-                Ns += __shfl_xor_sync(0xFFFFFFFFu, Ns, o);
-                accA += __shfl_xor_sync(0xFFFFFFFFu, accA, o);
-            }
-            // 2 * sum|T - amp| = 65535 * bf - 65534 * U + 2 * Xn       (mark_diff < space_diff :346-351)
-            // so 2 * (S - M) = 65534 * (Um - Us) + 2 * (Ns - Nm) with |Ns - Nm| <= bf: the sign of
-            // Um - Us decides unless the correlations tie, and only then is the floor compared.
-            const int du = Um - Us;
-            bool b1 = du > 0;
-            if (du == 0 && Ns > Nm) {
-                const int M2 = 65535 * bf - 65534 * Um + 2 * Nm;
-                const int S2 = M2 + 2 * (Ns - Nm);
-                b1 = (S2 - M2 >= two_bf) || (M2 < (S2 / two_bf) * two_bf);   // floor(M/bf) < floor(S/bf)
+                for (int o = 1; o < tpw; o <<= 1) {
+                    Um += __shfl_xor_sync(0xFFFFFFFFu, Um, o);
+                    Nm += __shfl_xor_sync(0xFFFFFFFFu, Nm, o);
+                    Us += __shfl_xor_sync(0xFFFFFFFFu, Us, o);
+                    Ns += __shfl_xor_sync(0xFFFFFFFFu, Ns, o);
+                    accA += __shfl_xor_sync(0xFFFFFFFFu, accA, o);
+                }
+                // 2 * sum|T - amp| = 65535 * bf - 65534 * U + 2 * Xn       (mark_diff < space_diff :346-351)
+                // so 2 * (S - M) = 65534 * (Um - Us) + 2 * (Ns - Nm) with |Ns - Nm| <= bf: the sign of
+                // Um - Us decides unless the correlations tie, and only then is the floor compared.
+                const int du = Um - Us;
+                b1 = du > 0;
+                if (du == 0 && Ns > Nm) {
+                    const int M2 = 65535 * bf - 65534 * Um + 2 * Nm;
+                    const int S2 = M2 + 2 * (Ns - Nm);
+                    b1 = (S2 - M2 >= two_bf) || (M2 < (S2 / two_bf) * two_bf);   // floor(M/bf) < floor(S/bf)
+                }
             }
             const bool valid = (part == 0) && (w < m.nwin);
             bit = valid && b1;
@@ -532,23 +674,6 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
 // vector i, slots < e from vector i+1), the +/-1 weights are uniform over the tile (alignment e is
 // per tile) and live in registers, and threads visit their windows in a lane-rotated order so that
 // the 128-bit shared-memory loads of a warp fall in different banks.
-__device__ __forceinline__ void accum4_full(uint32_t w0, uint32_t w1, uint32_t mw, uint32_t sw, uint32_t k512,
-                                            int &accM, int &accS, int &accA)
-{
-    const uint32_t g0 = __viaddmin_u16x2(w0, k512, 0x04010401u);
-    const uint32_t g1 = __viaddmin_u16x2(w1, k512, 0x04010401u);
-    const uint32_t t0 = g0 + 0x7BFF7BFFu;
-    const uint32_t t1 = g1 + 0x7BFF7BFFu;
-    const uint32_t s4 = prmt(w0, w1, 0xFDB9u);
-    const uint32_t nz4 = prmt(t0, t1, 0xFDB9u);
-    const uint32_t sg4 = s4 | 0x01010101u;
-    const uint32_t v4 = nz4 & sg4;
-    accM = dp4a_us(v4, mw, accM);
-    accS = dp4a_us(v4, sw, accS);
-    accA = __dp2a_lo((int)w0, (int)sg4, accA);
-    accA = __dp2a_hi((int)w1, (int)sg4, accA);
-}
-
 template <int kM, int kWpt>
 __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodParams p)
 {
@@ -592,30 +717,28 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodPar
     }
     __syncthreads();
 
-    const int per = (p.total_items + gridDim.x - 1) / gridDim.x;
-    const int lo = blockIdx.x * per;
-    const int hi = min(p.total_items, lo + per);
-    if (lo >= hi) return;
+    const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
+    if (ntile <= 0) return;
     if (warp == kConsumerThreads / 32) {
-        if (lane == 0) demod_produce(p, lo, hi, stage_base, meta, full, empty);
+        demod_produce(p, ntile, stage_base, meta, full, empty);
         return;
     }
 
     const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
     int s = 0;
     uint32_t ph = 0;
-    for (int n = 0; n < hi - lo; ++n) {
+    for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
         uint32_t bits = 0, quiet = 0;
         if (m.nwin > 0) {
-            const uint4 *wt = wtab + m.e0 * (kM + 1);
+            const uint4 *wt = wtab + (m.e0 & 7) * (kM + 1);
             uint4 W[kM];
 #pragma unroll
             for (int i = 0; i < kM; i++) W[i] = wt[i];
             const uint4 sel = wt[kM];
-            // e0 < 8 and kSeg % 8 == 0: the thread's first vector is tid * kSeg / 8
-            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + tid * (kSeg / 8);
+            // kSeg % 8 == 0: the thread's first vector is e0 / 8 + tid * kSeg / 8
+            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) + tid * (kSeg / 8);
 #pragma unroll
             for (int j = 0; j < kWpt; j++) {
                 const int jj = (j + tid) & (kWpt - 1);           // lane-rotated window order
@@ -868,8 +991,8 @@ struct Group {
     int small_wpt = 0;            // > 0: k_demod_small<bf/8, small_wpt>
     size_t smem = 0;
     int grid = 0;
-    std::vector<int32_t> caps, tile_first;
-    int32_t *d_caps = nullptr, *d_tile_first = nullptr;
+    std::vector<int32_t> caps, tile_first, tile_gpos;
+    int32_t *d_caps = nullptr, *d_tile_first = nullptr, *d_tile_gpos = nullptr;
 };
 
 }  // namespace
@@ -918,6 +1041,13 @@ struct AfskRxPlan {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
 
+// shared-memory ring of two CTAs per SM (228 KB per SM, 1 KB reserved per CTA).  Measured in one
+// process on config 2 (tools/ab_demod.py): 2 stages 6204 GB/s, 3 stages 6760, 4 stages 6690, 5 stages
+// 6513 — deeper rings do not help once the consumers keep up, so three it is (AFSK_DEMOD_STAGES
+// overrides, for tuning runs).
+constexpr size_t kDemodSmemBudget = 108 * 1024;
+constexpr size_t kDemodMaxStages = 3;
+
 static size_t demod_smem_bytes(const Group &g)
 {
     if (g.small_wpt)
@@ -925,6 +1055,15 @@ static size_t demod_smem_bytes(const Group &g)
                2 * kMaxStages * sizeof(uint64_t);
     return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * (8 * (2 * g.nt + 1) + 1) * 16 +
            kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t) + 2 * kConsumerThreads;
+}
+
+static int pick_stages(int stage_bytes)
+{
+    const size_t fit = std::max<size_t>(1, kDemodSmemBudget / (size_t)stage_bytes);
+    size_t want = kDemodMaxStages;
+    const char *ev = getenv("AFSK_DEMOD_STAGES");
+    if (ev && atoi(ev) > 0) want = (size_t)atoi(ev);
+    return (int)std::min<size_t>(std::min<size_t>(want, fit), kMaxStages);
 }
 
 static bool configure_group(Group &g, int bf)
@@ -938,9 +1077,8 @@ static bool configure_group(Group &g, int bf)
         g.nv = g.seg / 8 + 1;
         g.nt = g.nv; g.merge = 0;
         g.wt = kConsumerThreads * g.small_wpt;
-        g.stage_bytes = ((g.wt * bf * 2 + 16 + 128) + 127) & ~127;
-        const size_t budget_s = 100 * 1024;
-        g.stages = (int)std::min<size_t>(4, std::max<size_t>(1, budget_s / g.stage_bytes));
+        g.stage_bytes = ((g.wt * bf * 2 + 16 + 256) + 127) & ~127;
+        g.stages = pick_stages(g.stage_bytes);
         g.smem = demod_smem_bytes(g);
         return true;
     }
@@ -951,10 +1089,13 @@ static bool configure_group(Group &g, int bf)
     g.merge = (g.seg % 8 == 0 && g.seg <= 48) ? 1 : 0;   // then bf == tpw * seg and nv == seg/8 + 1
     g.nt = g.merge ? g.nv - 1 : g.nv;
     g.wt = kConsumerThreads / tpw;
-    g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 128) + 127) & ~127;   // copy + over-read slack
-    const size_t budget = 100 * 1024;   // two CTAs per SM
-    g.stages = (int)std::min<size_t>(4, std::max<size_t>(1, budget / g.stage_bytes));
+    g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 256) + 127) & ~127;   // copy (e0 < 64) + over-read slack
+    g.stages = pick_stages(g.stage_bytes);
     g.smem = demod_smem_bytes(g);
+    while (g.smem > 113 * 1024 && g.stages > 2) {      // keep two CTAs per SM when the tables are large
+        g.stages--;
+        g.smem = demod_smem_bytes(g);
+    }
     while (g.smem > 227 * 1024 && g.stages > 1) {
         g.stages--;
         g.smem = demod_smem_bytes(g);
@@ -1027,6 +1168,7 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
             P->max_windows = std::max(P->max_windows, kmax);
             if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
             g.caps.push_back(c);
+            g.tile_gpos.insert(g.tile_gpos.end(), (size_t)ntiles, (int32_t)g.caps.size() - 1);
             g.tile_first.push_back(g.tile_first.back() + (int32_t)ntiles);
             words += ntiles * (g.wt / 32) + 4;
             cap_bytes = (kmax / 14 + 16 + 15) & ~(int64_t)15;
@@ -1046,6 +1188,8 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
     for (Group &g : P->groups) {
         up((void **)&g.d_caps, g.caps.data(), sizeof(int32_t) * g.caps.size());
         up((void **)&g.d_tile_first, g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());
+        up((void **)&g.d_tile_gpos, g.tile_gpos.data(), sizeof(int32_t) * g.tile_gpos.size());
+        g.tile_gpos.clear(); g.tile_gpos.shrink_to_fit();
         const int total = g.tile_first.back();
         const int per_sm = g.smem <= 113 * 1024 ? 2 : 1;
         g.grid = std::max(1, std::min(total, P->sm_count * per_sm));
@@ -1066,7 +1210,7 @@ int afsk_rx_plan_destroy(AfskRxPlan *P)
     AfskDeviceGuard guard(P->device);
     for (auto &ev : P->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(P->d_caps); cudaFree(P->d_clock); cudaFree(P->d_planes);
-    for (Group &g : P->groups) { cudaFree(g.d_caps); cudaFree(g.d_tile_first); }
+    for (Group &g : P->groups) { cudaFree(g.d_caps); cudaFree(g.d_tile_first); cudaFree(g.d_tile_gpos); }
     delete P;
     return AFSK_OK;
 }
@@ -1135,7 +1279,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     for (const Group &g : P->groups) {
         DemodParams p;
         p.samples = d_samples; p.caps = P->d_caps; p.clock = P->d_clock;
-        p.gcaps = g.d_caps; p.gtile_first = g.d_tile_first;
+        p.gcaps = g.d_caps; p.gtile_first = g.d_tile_first; p.tile_gpos = g.d_tile_gpos;
         p.planes = P->d_planes;
         p.ng = (int)g.caps.size(); p.total_items = g.tile_first.back();
         p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.nt = g.nt; p.merge = g.merge; p.wt = g.wt;

@@ -22,9 +22,9 @@ SYMBOLS = [
     "afsk_abi_version", "afsk_last_error", "afsk_device_count", "afsk_device_info", "afsk_malloc",
     "afsk_free", "afsk_host_alloc", "afsk_host_free", "afsk_memcpy_h2d", "afsk_memcpy_d2h",
     "afsk_memset", "afsk_stream_create", "afsk_stream_destroy", "afsk_stream_sync",
-    "afsk_tone_lengths", "afsk_rx_plan_create", "afsk_rx_plan_destroy", "afsk_rx_plan_out_offsets",
+    "afsk_tone_lengths", "afsk_rx_plan_create", "afsk_rx_plan_create_ranges", "afsk_rx_plan_destroy", "afsk_rx_plan_out_offsets",
     "afsk_rx_plan_launches", "afsk_rx_plan_set_timing", "afsk_rx_plan_demod_time", "afsk_rx_decode", "afsk_rx_plan_planes", "afsk_rx_decode_host",
-    "afsk_rx_out_capacity", "afsk_rx_gate", "afsk_tx_num_samples", "afsk_tx_plan_create",
+    "afsk_rx_out_capacity", "afsk_rx_gate", "afsk_rx_gate_multi", "afsk_tx_num_samples", "afsk_tx_plan_create",
     "afsk_tx_plan_destroy", "afsk_tx_plan_out_offsets", "afsk_tx_synth", "afsk_tx_synth_host",
 ]
 
@@ -74,6 +74,7 @@ def lib():
     L.afsk_stream_sync.argtypes = [C.c_int, vp]
     L.afsk_tone_lengths.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.afsk_rx_plan_create.argtypes = [C.c_int, C.c_int, i64p, i32p, i32p, C.POINTER(vp)]
+    L.afsk_rx_plan_create_ranges.argtypes = [C.c_int, C.c_int, i64p, i64p, i32p, i32p, C.POINTER(vp)]
     L.afsk_rx_plan_destroy.argtypes = [vp]
     L.afsk_rx_plan_out_offsets.argtypes = [vp, C.POINTER(i64p)]
     L.afsk_rx_plan_launches.argtypes = [vp, C.POINTER(C.c_int)]
@@ -85,6 +86,7 @@ def lib():
     L.afsk_rx_out_capacity.argtypes = [C.c_int64, C.c_int]
     L.afsk_rx_out_capacity.restype = C.c_int64
     L.afsk_rx_gate.argtypes = [C.c_int, vp, i64p, C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp]
+    L.afsk_rx_gate_multi.argtypes = [C.c_int, vp, i64p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, vp, vp, vp]
     L.afsk_tx_num_samples.argtypes = [C.c_int, C.c_int64, C.c_int64, u8p]
     L.afsk_tx_num_samples.restype = C.c_int64
     L.afsk_tx_plan_create.argtypes = [C.c_int, C.c_int, i64p, i32p, i64p, u8p, C.POINTER(vp)]

@@ -986,6 +986,59 @@ __global__ void __launch_bounds__(kFrameThreads) k_gate_scan(const int32_t *__re
     }
 }
 
+// Successive Receiver.receive() calls over one recorded stream (the reference keeps its input stream
+// open between calls, afskmodem.py:283): every call discards one chunk (:303), examines up to
+// ceil(timeout / 2048) chunks for an opening (:304-310) and, once open, records through the first
+// chunk quieter than amp_end (:313-318); the next call starts at the chunk after.  One warp per
+// stream walks the chunk amplitudes 32 at a time.  Finite-stream conventions: a call that reaches
+// the end of the recording before opening or timing out does not return (the walk stops); a
+// recording still open at the end keeps everything up to the last full chunk.
+__device__ __forceinline__ long long warp_find_first(const int32_t *A, long long lo, long long hi, int thr, bool greater)
+{
+    const int lane = threadIdx.x & 31;
+    for (long long base = lo; base < hi; base += 32) {
+        const long long j = base + lane;
+        bool hit = false;
+        if (j < hi) {
+            const int a = A[j];
+            hit = greater ? (a > thr) : (a < thr);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (m) return base + (__ffs(m) - 1);
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(32) k_gate_multi(const int32_t *__restrict__ amp, const int64_t *__restrict__ chunk_first,
+                                                   int amp_start, int amp_end, long long timeout_frames, int max_calls,
+                                                   int64_t *__restrict__ ranges, int32_t *__restrict__ counts)
+{
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int32_t *A = amp + chunk_first[s];
+    const long long nch = chunk_first[s + 1] - chunk_first[s];
+    const long long lim = timeout_frames <= 0 ? 0 : (timeout_frames + AFSK_GATE_CHUNK - 1) / AFSK_GATE_CHUNK;
+    int64_t *out = ranges + (size_t)s * max_calls * 3;
+    long long pos = 0;
+    int calls = 0;
+    while (calls < max_calls && pos < nch) {
+        const long long first = pos + 1;                          // chunk `pos` is discarded :303
+        const long long open = warp_find_first(A, first, min(first + lim, nch), amp_start, true);   // :306
+        long long rec = 0, a = 0, b = 0;
+        if (open < 0) {
+            if (first + lim > nch) break;                         // recording ends before the timeout does
+            pos = first + lim;                                    // "Timed out." :311-312, :405-407
+        } else {
+            const long long close = warp_find_first(A, open + 1, nch, amp_end, false);               // :316
+            const long long end = close < 0 ? nch : close + 1;
+            rec = 1; a = open * AFSK_GATE_CHUNK; b = end * AFSK_GATE_CHUNK;
+            pos = end;
+        }
+        if (lane == 0) { out[3 * calls] = rec; out[3 * calls + 1] = a; out[3 * calls + 2] = b; }
+        calls++;
+    }
+    if (lane == 0) counts[s] = calls;
+}
+
 struct Group {
     int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, stage_bytes = 0, stages = 0;
     int small_wpt = 0;            // > 0: k_demod_small<bf/8, small_wpt>
@@ -1119,6 +1172,18 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
         afsk_set_error("afsk_rx_plan_create: bad argument");
         return AFSK_E_ARG;
     }
+    std::vector<int64_t> len((size_t)(B > 0 ? B : 0));
+    for (int c = 0; c < B; c++) len[c] = h_offsets[c + 1] - h_offsets[c];
+    return afsk_rx_plan_create_ranges(device, B, h_offsets, len.data(), h_baud, h_amp_end, plan_out);
+}
+
+int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const int64_t *h_len, const int32_t *h_baud,
+                               const int32_t *h_amp_end, AfskRxPlan **plan_out)
+{
+    if (!plan_out || B < 0 || (B > 0 && (!h_start || !h_len || !h_baud || !h_amp_end))) {
+        afsk_set_error("afsk_rx_plan_create_ranges: bad argument");
+        return AFSK_E_ARG;
+    }
     AfskDeviceGuard guard(device);
     if (!guard.ok) { afsk_set_error("cannot select device %d", device); return AFSK_E_CUDA; }
     AfskRxPlan *P = new (std::nothrow) AfskRxPlan();
@@ -1133,9 +1198,9 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
     int64_t words = 0;
     for (int c = 0; c < B; c++) {
         CapDesc &d = P->caps[c];
-        d.off = h_offsets[c];
-        d.n = h_offsets[c + 1] - h_offsets[c];
-        if (d.n < 0 || d.off < 0) { delete P; afsk_set_error("offsets must be non-decreasing"); return AFSK_E_ARG; }
+        d.off = h_start[c];
+        d.n = h_len[c];
+        if (d.n < 0 || d.off < 0) { delete P; afsk_set_error("capture %d: negative start or length (offsets must be non-decreasing)", c); return AFSK_E_ARG; }
         d.plane_base = words;
         d.out_off = P->out_off[c];
         d.group = -1;
@@ -1372,6 +1437,35 @@ int afsk_rx_gate(int device, const int16_t *d_samples, const int64_t *h_offsets,
         k_gate_amp<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_samples, d_first, d_off, S, total, d_amp);
     }
     k_gate_scan<<<S, kFrameThreads, 0, st>>>(d_amp, d_first, amp_start, amp_end, timeout_frames, d_range);
+    AFSK_CUDA(cudaGetLastError());
+    AFSK_CUDA(cudaStreamSynchronize(st));     // host staging vectors go out of scope
+    cudaFree(d_first); cudaFree(d_off); cudaFree(d_amp);
+    return AFSK_OK;
+}
+
+int afsk_rx_gate_multi(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start, int amp_end,
+                       int64_t timeout_frames, int max_calls, int64_t *d_ranges, int32_t *d_counts, void *stream)
+{
+    if (S < 0 || max_calls < 0 || (S > 0 && (!d_samples || !h_offsets || !d_ranges || !d_counts))) return AFSK_E_ARG;
+    if (S == 0) return AFSK_OK;
+    AfskDeviceGuard guard(device);
+    if (!guard.ok) return AFSK_E_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> first(S + 1, 0);
+    for (int s = 0; s < S; s++) first[s + 1] = first[s] + (h_offsets[s + 1] - h_offsets[s]) / AFSK_GATE_CHUNK;
+    const long long total = first[S];
+    int64_t *d_first = nullptr, *d_off = nullptr;
+    int32_t *d_amp = nullptr;
+    AFSK_CUDA(cudaMalloc((void **)&d_first, sizeof(int64_t) * (S + 1)));
+    AFSK_CUDA(cudaMalloc((void **)&d_off, sizeof(int64_t) * (S + 1)));
+    AFSK_CUDA(cudaMalloc((void **)&d_amp, sizeof(int32_t) * (total ? total : 1)));
+    AFSK_CUDA(cudaMemcpyAsync(d_first, first.data(), sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
+    AFSK_CUDA(cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
+    if (total > 0) {
+        const int wpb = 8;
+        k_gate_amp<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_samples, d_first, d_off, S, total, d_amp);
+    }
+    k_gate_multi<<<S, 32, 0, st>>>(d_amp, d_first, amp_start, amp_end, timeout_frames, max_calls, d_ranges, d_counts);
     AFSK_CUDA(cudaGetLastError());
     AFSK_CUDA(cudaStreamSynchronize(st));     // host staging vectors go out of scope
     cudaFree(d_first); cudaFree(d_off); cudaFree(d_amp);

@@ -29,9 +29,11 @@ struct __align__(16) TxDesc {
     int64_t out_len;      // frames written by save(): (len(frames) & ~1)
     int64_t total_bits;   // training + terminator + coded bits
     int64_t ts_bits;      // 2 * ts_cycles training bits (1,0,1,0,...)
-    int32_t bf;
-    int32_t pad;
+    int32_t bf;           // = space tone length
+    int32_t ml;           // mark tone length: bf, or bf - 2 when bf % 4 == 2 (4800, 960, 1600, 8000, 24000 baud)
     int64_t chunk_first;  // first CTA chunk of this capture
+    int64_t nib_off;      // ml != bf: offset of the capture's nibble start table (2 * pay_len + 1 entries)
+    int64_t pad;
 };
 
 // Hamming(7,4) generator (ECC.__M_GENERATOR :115-123): codeword bit r of nibble v, LSB = c0
@@ -71,7 +73,7 @@ __device__ __forceinline__ uint32_t tone_pair(uint32_t sym, int ph, int bf)
     if (sym == 2u) return 0u;
     const int q = bf >> 2, h = bf >> 1;
     bool hi;
-    if (sym) hi = (ph < q) || (ph >= h && ph < h + q);       // mark : q HI, q LO, q HI, q LO
+    if (sym) hi = (ph < q) || (ph >= 2 * q && ph < 3 * q);   // mark : q HI, q LO, q HI, q LO  (q = int(bf / 4))
     else hi = ph < h;                                        // space: h HI, h LO
     return hi ? 0x7FFF7FFFu : 0x80008000u;
 }
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(kSynthThreads) k_synth(const uint8_t *__restri
     const int tid = threadIdx.x;
     const long long chunk = blockIdx.x;
     const TxDesc d = descs[chunk_cap[chunk]];
+    if (d.ml != d.bf) return;                                // unequal tones: k_synth_var
     const int bf = d.bf;
     const int G = (bf & 7) ? 2 : 1;                          // bits per group
     const int VG = G * bf / 8;                               // vectors per group
@@ -139,6 +142,114 @@ __global__ void __launch_bounds__(kSynthThreads) k_synth(const uint8_t *__restri
     }
 }
 
+// ------------------------------------------------------------------ unequal tone lengths ----
+// When bit_frames % 4 == 2 the mark tone (two cycles of int(bf/4) HI + int(bf/4) LO, :81-85) is two
+// frames shorter than the space tone, so a bit's first frame depends on how many marks precede it
+// (__getFrames :463-467 just appends).  k_tx_nibscan writes the first frame of every Hamming
+// codeword (exclusive scan of ones * ml + (7 - ones) * bf over the nibbles), k_synth_var locates
+// each output vector's frames by binary search in that table and walks the 7 bits of the codeword.
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads) k_tx_nibscan(const uint8_t *__restrict__ pay,
+                                                            const TxDesc *__restrict__ descs,
+                                                            const int32_t *__restrict__ var_caps,
+                                                            int64_t *__restrict__ nib_start)
+{
+    const TxDesc d = descs[var_caps[blockIdx.x]];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ long long warp_tot[kScanThreads / 32];
+    int64_t *out = nib_start + d.nib_off;
+    const long long G = 2 * d.pay_len;
+    long long carry = 0;
+    for (long long base = 0; base <= G; base += kScanThreads) {
+        const long long g = base + tid;
+        long long len = 0;
+        if (g < G) {
+            const uint32_t byte = pay[d.pay_off + (g >> 1)];
+            const int ones = __popc(hamming74_encode((g & 1) ? (byte & 15u) : (byte >> 4)));
+            len = (long long)ones * d.ml + (long long)(7 - ones) * d.bf;
+        }
+        long long inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        long long before = carry, total = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) {
+            if (w < warp) before += warp_tot[w];
+            total += warp_tot[w];
+        }
+        if (g <= G) out[g] = before + inc - len;             // exclusive: first frame of codeword g
+        carry += total;
+        __syncthreads();
+    }
+}
+
+// frame n of a capture with unequal tones, as the duplicated pair SoundOutput.__convertFrames emits
+__device__ __forceinline__ uint32_t var_frame_pair(long long n, const TxDesc &d, const uint8_t *__restrict__ pay,
+                                                   const int64_t *__restrict__ ns, long long &g)
+{
+    const long long ml = d.ml, sl = d.bf;
+    const long long T0 = (d.ts_bits >> 1) * (ml + sl);       // training cycles: mark, space  :457-458
+    if (n < T0) {
+        const long long r = n % (ml + sl);
+        return r < ml ? tone_pair(1u, (int)r, d.bf) : tone_pair(0u, (int)(r - ml), d.bf);
+    }
+    long long t = n - T0;
+    if (t < ml) return tone_pair(1u, (int)t, d.bf);          // terminator: mark, space x3   :460-462
+    t -= ml;
+    if (t < 3 * sl) return tone_pair(0u, (int)(t % sl), d.bf);
+    t -= 3 * sl;
+    const long long G = 2 * d.pay_len;
+    if (G == 0 || t >= ns[G]) return 0u;                     // 4800 zero frames :468
+    if (g < 0) {                                             // last codeword starting at or before t
+        long long a = 0, b = G;
+        while (b - a > 1) {
+            const long long mid = (a + b) >> 1;
+            if (ns[mid] <= t) a = mid; else b = mid;
+        }
+        g = a;
+    }
+    while (ns[g + 1] <= t) g++;
+    long long u = t - ns[g];
+    const uint32_t byte = pay[d.pay_off + (g >> 1)];
+    const uint32_t cw = hamming74_encode((g & 1) ? (byte & 15u) : (byte >> 4));
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        const uint32_t bit = (cw >> r) & 1u;
+        const long long L = bit ? ml : sl;
+        if (u < L) return tone_pair(bit, (int)u, d.bf);
+        u -= L;
+    }
+    return 0u;                                               // unreachable: t < ns[g + 1]
+}
+
+__global__ void __launch_bounds__(kSynthThreads) k_synth_var(const uint8_t *__restrict__ pay,
+                                                             const TxDesc *__restrict__ descs,
+                                                             const int32_t *__restrict__ chunk_cap,
+                                                             const int64_t *__restrict__ nib_start,
+                                                             int16_t *__restrict__ out)
+{
+    const long long chunk = blockIdx.x;
+    const TxDesc d = descs[chunk_cap[chunk]];
+    if (d.ml == d.bf) return;                                // equal tones: k_synth
+    const int64_t *ns = nib_start + d.nib_off;
+    const long long nvec_cap = (d.out_len + 7) >> 3;
+    const long long v0 = (chunk - d.chunk_first) * kChunkVecs;
+    const long long vend = min(v0 + (long long)kChunkVecs, nvec_cap);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + d.out_off);
+    for (long long vi = v0 + threadIdx.x; vi < vend; vi += kSynthThreads) {
+        long long g = -1;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = var_frame_pair(8 * vi + 2 * j, d, pay, ns, g);
+        dst[vi] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 static size_t synth_smem_bytes(int bf)
 {
     const int G = (bf & 7) ? 2 : 1, VG = G * bf / 8;
@@ -157,6 +268,11 @@ struct AfskTxPlan {
     std::vector<int32_t> chunk_cap;
     int64_t total_chunks = 0;
     size_t smem = 0;
+    std::vector<int32_t> var_caps;       // captures with unequal mark/space tone lengths
+    int32_t *d_var_caps = nullptr;
+    int64_t *d_nib_start = nullptr;
+    int64_t nib_entries = 0;
+    bool has_equal = false;
 };
 
 extern "C" {
@@ -186,7 +302,6 @@ int64_t afsk_tx_num_samples(int baud, int64_t ts_cycles, int64_t payload_bytes, 
 int afsk_tx_plan_create(int device, int B, const int64_t *h_pay_off, const int32_t *h_baud, const int64_t *h_ts_cycles,
                         const uint8_t *h_payload, AfskTxPlan **plan_out)
 {
-    (void)h_payload;
     if (!plan_out || B < 0 || (B > 0 && (!h_pay_off || !h_baud || !h_ts_cycles))) return AFSK_E_ARG;
     AfskDeviceGuard guard(device);
     if (!guard.ok) { afsk_set_error("cannot select device %d", device); return AFSK_E_CUDA; }
@@ -203,22 +318,31 @@ int afsk_tx_plan_create(int device, int B, const int64_t *h_pay_off, const int32
         if (!afsk_tone_geometry(h_baud[c], &bf, &ml, &sl)) {
             delete P; afsk_set_error("Invalid baud rate."); return AFSK_E_BAUD;
         }
-        if (ml != sl) {
-            delete P;
-            afsk_set_error("baud %d has unequal mark/space tone lengths (%d/%d): not supported by the GPU synthesizer yet",
-                           h_baud[c], ml, sl);
-            return AFSK_E_UNSUPPORTED;
-        }
         TxDesc &d = P->descs[c];
         const int64_t ts = h_ts_cycles[c] < 0 ? 0 : h_ts_cycles[c];
         d.pay_off = h_pay_off[c];
         d.pay_len = h_pay_off[c + 1] - h_pay_off[c];
         if (d.pay_len < 0) { delete P; afsk_set_error("payload offsets must be non-decreasing"); return AFSK_E_ARG; }
-        d.bf = bf; d.pad = 0;
+        d.bf = bf; d.ml = ml; d.pad = 0; d.nib_off = 0;
         d.ts_bits = 2 * ts;
         d.total_bits = d.ts_bits + 4 + 14 * d.pay_len;
-        d.out_len = (d.total_bits * bf + AFSK_TAIL_FRAMES) & ~(int64_t)1;
-        P->smem = std::max(P->smem, synth_smem_bytes(bf));
+        if (ml == sl) {
+            d.out_len = (d.total_bits * bf + AFSK_TAIL_FRAMES) & ~(int64_t)1;
+            P->smem = std::max(P->smem, synth_smem_bytes(bf));
+            P->has_equal = true;
+        } else {
+            // the length depends on how many mark bits the codewords hold: the plan is made for THIS payload
+            if (d.pay_len > 0 && !h_payload) {
+                delete P; afsk_set_error("afsk_tx_plan_create: the payload is needed for baud %d (unequal tone lengths)", h_baud[c]);
+                return AFSK_E_ARG;
+            }
+            const int64_t nf = afsk_tx_num_samples(h_baud[c], ts, d.pay_len, h_payload ? h_payload + d.pay_off : nullptr);
+            if (nf < 0) { delete P; return (int)nf; }
+            d.out_len = nf;
+            d.nib_off = P->nib_entries;
+            P->nib_entries += 2 * d.pay_len + 1;
+            P->var_caps.push_back(c);
+        }
         d.out_off = P->out_off[c];
         d.chunk_first = chunks;
         const int64_t nvec = (d.out_len + 7) >> 3;
@@ -238,6 +362,11 @@ int afsk_tx_plan_create(int device, int B, const int64_t *h_pay_off, const int32
     if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_chunk_cap, sizeof(int32_t) * (chunks ? chunks : 1));
     if (e == cudaSuccess && chunks)
         e = cudaMemcpy(P->d_chunk_cap, P->chunk_cap.data(), sizeof(int32_t) * chunks, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !P->var_caps.empty()) {
+        e = cudaMalloc((void **)&P->d_var_caps, sizeof(int32_t) * P->var_caps.size());
+        if (e == cudaSuccess) e = cudaMemcpy(P->d_var_caps, P->var_caps.data(), sizeof(int32_t) * P->var_caps.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_nib_start, sizeof(int64_t) * P->nib_entries);
+    }
     if (e != cudaSuccess) {
         afsk_set_error("afsk_tx_plan_create: %s", cudaGetErrorString(e));
         afsk_tx_plan_destroy(P);
@@ -253,6 +382,8 @@ int afsk_tx_plan_destroy(AfskTxPlan *P)
     AfskDeviceGuard guard(P->device);
     cudaFree(P->d_descs);
     cudaFree(P->d_chunk_cap);
+    cudaFree(P->d_var_caps);
+    cudaFree(P->d_nib_start);
     delete P;
     return AFSK_OK;
 }
@@ -272,7 +403,13 @@ int afsk_tx_synth(AfskTxPlan *P, const uint8_t *d_payload, int16_t *d_out, void 
     if (P->B == 0 || P->total_chunks == 0) return AFSK_OK;
     AfskDeviceGuard guard(P->device);
     if (!guard.ok) return AFSK_E_CUDA;
-    k_synth<<<(unsigned)P->total_chunks, kSynthThreads, P->smem, (cudaStream_t)stream>>>(d_payload, P->d_descs, P->d_chunk_cap, d_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P->has_equal)
+        k_synth<<<(unsigned)P->total_chunks, kSynthThreads, P->smem, st>>>(d_payload, P->d_descs, P->d_chunk_cap, d_out);
+    if (!P->var_caps.empty()) {
+        k_tx_nibscan<<<(unsigned)P->var_caps.size(), kScanThreads, 0, st>>>(d_payload, P->d_descs, P->d_var_caps, P->d_nib_start);
+        k_synth_var<<<(unsigned)P->total_chunks, kSynthThreads, 0, st>>>(d_payload, P->d_descs, P->d_chunk_cap, P->d_nib_start, d_out);
+    }
     AFSK_CUDA(cudaGetLastError());
     return AFSK_OK;
 }

@@ -168,18 +168,28 @@ class RxSession:
     ``d_samples`` may be an external device pointer (e.g. ``torch.Tensor.data_ptr()``).
     """
 
-    def __init__(self, offsets, baud, amp_end, device: int = 0):
+    def __init__(self, offsets, baud, amp_end, device: int = 0, lengths=None):
+        """``offsets``: CSR offsets (B+1) of adjacent captures, or — with ``lengths`` (B) — the start of
+        each capture inside one sample buffer (captures need not be adjacent)."""
         _cabi.require_device(device)
         L = _cabi.lib()
         self.device = device
         self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-        self.B = len(self.offsets) - 1
+        self.lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int64)
+        self.B = len(self.offsets) - 1 if self.lengths is None else len(self.lengths)
         self.baud = np.ascontiguousarray(np.broadcast_to(np.asarray(baud, dtype=np.int32), (self.B,)))
         self.amp_end = np.ascontiguousarray(np.broadcast_to(np.asarray(amp_end, dtype=np.int32), (self.B,)))
         plan = C.c_void_p()
-        _cabi.check(L.afsk_rx_plan_create(device, self.B, _cabi.ptr(self.offsets, C.c_int64),
-                                          _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
-                                          C.byref(plan)))
+        if self.lengths is None:
+            _cabi.check(L.afsk_rx_plan_create(device, self.B, _cabi.ptr(self.offsets, C.c_int64),
+                                              _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
+                                              C.byref(plan)))
+        else:
+            assert len(self.offsets) == self.B
+            _cabi.check(L.afsk_rx_plan_create_ranges(device, self.B, _cabi.ptr(self.offsets, C.c_int64),
+                                                     _cabi.ptr(self.lengths, C.c_int64),
+                                                     _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
+                                                     C.byref(plan)))
         self.plan = plan
         po = C.POINTER(C.c_int64)()
         _cabi.check(L.afsk_rx_plan_out_offsets(plan, C.byref(po)))
@@ -187,7 +197,10 @@ class RxSession:
         n = C.c_int(0)
         _cabi.check(L.afsk_rx_plan_launches(plan, C.byref(n)))
         self.launches = n.value
-        self.total_samples = int(self.offsets[-1])
+        if self.lengths is None:
+            self.total_samples = int(self.offsets[-1])
+        else:
+            self.total_samples = int((self.offsets + self.lengths).max()) if self.B else 0
         self.d_out = DeviceBuffer(device, int(self.out_off[-1]))
         self.d_res = DeviceBuffer(device, 32 * max(self.B, 1))
         self.d_samples = None
@@ -404,6 +417,86 @@ class Receiver:
         self._log.debug("Recording finished")
         frames = np.asarray(stream_samples, dtype=np.int16)[a:b]
         return self.to_python(self.decode_batch([frames]), 0, string)
+
+    def listen_gate_multi(self, stream_samples, timeout: float, device: int | None = None, d_samples=None):
+        """Successive ``__listen`` calls (:299-319) of one receiver over ONE recorded stream →
+        [(recorded, start, end), ...], one entry per ``receive`` call that returns before the
+        recording ends (recorded False = "Timed out.")."""
+        x = np.ascontiguousarray(stream_samples, dtype=np.int16)
+        dev = self._device if device is None else device
+        _cabi.require_device(dev)
+        max_calls = max(1, len(x) // 2048)
+        offsets = np.array([0, len(x)], dtype=np.int64)
+        own = d_samples is None
+        d_s = DeviceBuffer(dev, len(x) * 2 + 32) if own else d_samples
+        d_r = DeviceBuffer(dev, 24 * max_calls)
+        d_c = DeviceBuffer(dev, 16)
+        try:
+            if own:
+                d_s.upload(x)
+            _cabi.check(_cabi.lib().afsk_rx_gate_multi(dev, C.c_void_p(d_s.ptr), _cabi.ptr(offsets, C.c_int64), 1,
+                                                       int(np.floor(self._amp_start)), _as_int_threshold(self._amp_end),
+                                                       int(timeout * 48000), max_calls, C.c_void_p(d_r.ptr),
+                                                       C.c_void_p(d_c.ptr), None))
+            cnt = np.zeros(4, dtype=np.int32)
+            d_c.download(cnt)
+            _cabi.stream_sync(dev)
+            r = np.zeros((max(int(cnt[0]), 1), 3), dtype=np.int64)
+            if cnt[0]:
+                d_r.download(r)
+                _cabi.stream_sync(dev)
+        finally:
+            if own:
+                d_s.close()
+            d_r.close()
+            d_c.close()
+        return [(bool(a), int(b), int(c)) for a, b, c in r[:int(cnt[0])]]
+
+    def receive_all(self, stream_samples, timeout: float, string: bool = True, keep_timeouts: bool = False,
+                    errors: str = "raise") -> list:
+        """What successive ``receive(timeout, string)`` calls (:402-417) of one receiver return over a
+        recorded int16 stream holding any number of transmissions: the stream is uploaded once, the
+        listen gate cuts it into recordings on the GPU, all recordings are decoded as one batch.
+        Timed-out calls (``b""``) are dropped unless ``keep_timeouts``."""
+        x = np.ascontiguousarray(stream_samples, dtype=np.int16)
+        dev = self._device
+        _cabi.require_device(dev)
+        d_s = DeviceBuffer(dev, (len(x) * 2 + 15) // 16 * 16 + 32)
+        try:
+            d_s.upload(x)
+            calls = self.listen_gate_multi(x, timeout, dev, d_samples=d_s)
+            recs = [(a, b) for rec, a, b in calls if rec]
+            batch = None
+            if recs:
+                sess = RxSession(np.array([a for a, _ in recs], dtype=np.int64), self._baud,
+                                 _as_int_threshold(self._amp_end), dev,
+                                 lengths=np.array([b - a for a, b in recs], dtype=np.int64))
+                try:
+                    sess.bind(d_s.ptr)
+                    sess.run()
+                    batch = sess.download()
+                finally:
+                    sess.close()
+        finally:
+            d_s.close()
+        out, k = [], 0
+        for rec, _, _ in calls:
+            self._log.info("Listening...")
+            if not rec:
+                self._log.warn("Timed out.")
+                if keep_timeouts:
+                    out.append(b"")
+                continue
+            self._log.debug("Recording started")
+            self._log.debug("Recording finished")
+            try:
+                out.append(self.to_python(batch, k, string))
+            except Exception as e:  # noqa: BLE001 - mirrors whatever receive raises
+                if errors == "raise":
+                    raise
+                out.append(e)
+            k += 1
+        return out
 
     def receive(self, timeout: float, string: bool = True) -> bytes | str:
         """Live microphone path (:402-417).  Needs an audio device; out of scope for the GPU core —

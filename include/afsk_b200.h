@@ -95,6 +95,10 @@ int afsk_tone_lengths(int baud, int *bit_frames, int *mark_len, int *space_len);
  */
 int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32_t *h_baud,
                         const int32_t *h_amp_end, AfskRxPlan **plan);
+/* same, for captures given as arbitrary (possibly non-adjacent) [start, start + len) ranges of one
+ * sample buffer — e.g. the recordings afsk_rx_gate_multi cuts out of a long stream */
+int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const int64_t *h_len,
+                               const int32_t *h_baud, const int32_t *h_amp_end, AfskRxPlan **plan);
 int afsk_rx_plan_destroy(AfskRxPlan *plan);
 /* capacity offsets (bytes, B+1 entries, host memory owned by the plan) of the decoded output */
 int afsk_rx_plan_out_offsets(const AfskRxPlan *plan, const int64_t **h_out_off);
@@ -137,6 +141,17 @@ int64_t afsk_rx_out_capacity(int64_t n_samples, int baud);
  */
 int afsk_rx_gate(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start,
                  int amp_end, int64_t timeout_frames, int64_t *d_range, void *stream);
+
+/*
+ * Successive Receiver.receive(timeout) calls of ONE receiver over each recorded stream (the
+ * reference keeps its input stream open between calls, afskmodem.py:283, so call k+1 starts at the
+ * chunk after call k's last read): per call one int64 triple {recorded(0 = "Timed out."), start, end}
+ * in d_ranges[s * max_calls * 3 ...], calls made per stream in d_counts[s].  A call that reaches
+ * the end of the recording before opening or timing out is not reported.
+ */
+int afsk_rx_gate_multi(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start,
+                       int amp_end, int64_t timeout_frames, int max_calls, int64_t *d_ranges,
+                       int32_t *d_counts, void *stream);
 
 /* ---------------------------------------------------------------- transmitter ---------- */
 /* frames Transmitter.save writes for a payload of n bytes (afskmodem.py:452-469 then :239-244).

@@ -361,6 +361,49 @@ int afsk_oracle_listen_gate(const int16_t *s, int64_t n, int amp_start, int amp_
     return 1;
 }
 
+/* Successive Receiver.receive() calls of one receiver over one recorded stream: __listen :299-319
+ * restarted at the chunk after the previous call's last read (the input stream stays open between
+ * calls, :283).  out[3k..3k+2] = {recorded, start, end} of call k ("Timed out." → 0,0,0).  A call
+ * that runs off the end of the recording before opening or timing out is not reported (the
+ * reference would block in stream.read); a recording still open at the end keeps every full chunk. */
+int64_t afsk_oracle_listen_gate_multi(const int16_t *s, int64_t n, int amp_start, int amp_end,
+                                      int64_t timeout_frames, int64_t max_calls, int64_t *out)
+{
+    int64_t nchunks = n / 2048, idx = 0, calls = 0;
+    while (calls < max_calls) {
+        if (idx >= nchunks) break;
+        idx++;                                                   /* :303 discard */
+        int64_t listened = 0, start = 0, end = 0;
+        int opened = 0, eof = 0;
+        while (listened < timeout_frames) {                      /* :304 */
+            if (idx >= nchunks) { eof = 1; break; }
+            const int16_t *fr = s + idx * 2048; idx++;           /* :305 */
+            if (afsk_oracle_amplitude(fr, 2048) > amp_start) {   /* :306 */
+                start = (idx - 1) * 2048;
+                opened = 1;
+                break;
+            }
+            listened += 2048;                                    /* :310 */
+        }
+        if (eof) break;
+        if (!opened) {                                           /* :311-312 → "Timed out." :405-407 */
+            out[3 * calls] = 0; out[3 * calls + 1] = 0; out[3 * calls + 2] = 0;
+            calls++;
+            continue;
+        }
+        end = idx * 2048;
+        while (1) {                                              /* :313 */
+            if (idx >= nchunks) break;
+            const int16_t *fr = s + idx * 2048; idx++;           /* :314 */
+            end = idx * 2048;                                    /* :315 */
+            if (afsk_oracle_amplitude(fr, 2048) < amp_end) break;/* :316-318 */
+        }
+        out[3 * calls] = 1; out[3 * calls + 1] = start; out[3 * calls + 2] = end;
+        calls++;
+    }
+    return calls;
+}
+
 /* ---- Transmitter ---- */
 
 /* int(baud_rate * training_time / 2) :438 is evaluated in Python (float) by the caller. */

@@ -141,6 +141,18 @@ def listen_gate(stream: np.ndarray, amp_start: int, amp_end: int, timeout_frames
     return bool(ok), a.value, b.value
 
 
+def listen_gate_multi(stream: np.ndarray, amp_start: int, amp_end: int, timeout_frames: int, max_calls: int = 0):
+    """→ [(recorded?, start, end), ...] of successive Receiver.receive() calls over one recording."""
+    s = np.ascontiguousarray(stream, dtype=np.int16)
+    max_calls = max_calls or max(1, len(s) // 2048)
+    out = np.zeros((max_calls, 3), dtype=np.int64)
+    L = lib()
+    L.afsk_oracle_listen_gate_multi.restype = C.c_int64
+    n = L.afsk_oracle_listen_gate_multi(_p(s, C.c_int16), C.c_int64(len(s)), int(amp_start), int(amp_end),
+                                        C.c_int64(int(timeout_frames)), C.c_int64(max_calls), _p(out, C.c_int64))
+    return [(bool(a), int(b), int(c)) for a, b, c in out[:n]]
+
+
 def ts_cycles(baud: int, training_time: float) -> int:
     """Transmitter.__init__ afskmodem.py:438 (Python float arithmetic, truncation)."""
     return int(baud * training_time / 2)

@@ -149,3 +149,35 @@ def ref_receive(stream: np.ndarray, baud: int, amp_start: int, amp_end: int, tim
         pa.PyAudio.feed = None
     res.update(_scrape(buf.getvalue()))
     return res
+
+
+def ref_receive_many(stream: np.ndarray, baud: int, amp_start: int, amp_end: int, timeout: float,
+                     max_calls: int = 64) -> list[dict]:
+    """Successive ``Receiver.receive(timeout, False)`` calls of ONE Receiver over one recorded stream
+    (the reference keeps its input stream open between calls, afskmodem.py:283): one dict per call
+    until the feed is exhausted (the stub raises EOFError, which ends the list)."""
+    m = module()
+    pa = sys.modules[m.pyaudio.__name__]
+    m.LOG_LEVEL = 0
+    pa.PyAudio.feed = np.ascontiguousarray(stream, dtype="<i2").tobytes()
+    calls: list[dict] = []
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = m.Receiver(baud, amp_start, amp_end)
+        st = pa.PyAudio.last_stream
+        for _ in range(max_calls):
+            buf = io.StringIO()
+            res: dict = {"exc": None, "ret": None, "reads_before": st.reads}
+            with contextlib.redirect_stdout(buf):
+                try:
+                    res["ret"] = r.receive(timeout, False)
+                except EOFError:
+                    break
+                except Exception as e:  # noqa: BLE001
+                    res["exc"] = (type(e).__name__, str(e))
+            res["reads_after"] = st.reads
+            res.update(_scrape(buf.getvalue()))
+            calls.append(res)
+    finally:
+        pa.PyAudio.feed = None
+    return calls

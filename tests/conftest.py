@@ -31,6 +31,29 @@ def load_gate_golden():
     return json.load(open(os.path.join(GOLDEN, "gate_cases.json")))
 
 
+def load_gate_multi_golden():
+    return json.load(open(os.path.join(GOLDEN, "gate_multi_cases.json")))
+
+
+def gate_multi_stream(g, tx_frames):
+    """Rebuilds the recorded stream of a gate_multi golden case from its recipe; ``tx_frames(msg,
+    baud, training_time)`` must be sample-exact with the reference's Transmitter.save (checked by
+    the case's SHA-256)."""
+    import hashlib
+
+    import numpy as np
+    parts = []
+    for lead, msg, gain, tt in g["segments"]:
+        parts.append(np.zeros(lead, np.int16))
+        if msg is not None:
+            parts.append((tx_frames(msg.encode("utf-8"), g["baud"], tt).astype(np.float64) * gain).astype(np.int16))
+    s = np.concatenate(parts)
+    if g["cut"]:
+        s = s[:len(s) - g["cut"]]
+    assert len(s) == g["n"] and hashlib.sha256(s.astype("<i2").tobytes()).hexdigest() == g["sha256"], g["name"]
+    return s
+
+
 @pytest.fixture(scope="session")
 def rx_golden():
     return load_rx_golden()

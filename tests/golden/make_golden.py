@@ -1,4 +1,4 @@
-"""Generates tests/golden/{rx_cases.npz,rx_cases.json,tx_cases.npz,tx_cases.json,gate_cases.json}
+"""Generates tests/golden/{rx_cases.npz,rx_cases.json,tx_cases.npz,tx_cases.json,gate_cases.json,gate_multi_cases.json}
 by running the UNMODIFIED reference (/root/reference/afskmodem.py) in this container through
 oracle/ref_harness.py.  The reference ships no golden vectors of its own, so these
 files ARE the pin: the oracle (oracle/afsk_oracle.c) is checked against them on CPU, and the CUDA
@@ -167,7 +167,41 @@ def main():
                      "ret_hex": r["ret"].hex() if isinstance(r["ret"], (bytes, bytearray)) else None,
                      "clock": r["clock"], "train_end": r["train_end"], "nbits": r["nbits"]})
     json.dump(gate, open(os.path.join(HERE, "gate_cases.json"), "w"), indent=1)
-    for f in ("rx_cases.npz", "rx_cases.json", "tx_cases.npz", "tx_cases.json", "gate_cases.json"):
+
+    # several transmissions in one recording: successive receive() calls of ONE reference Receiver
+    multi = []
+    for name, baud, a0, a1, timeout, segs in [
+            # segs: (silence before, message, gain, training_time)
+            ("three_msgs", 1200, 18000, 14000, 100.0,
+             [(5000, "first message", 1.0, 0.1), (3000, "2nd", 1.0, 0.1), (20000, "the third and last one", 1.0, 0.1), (9000, None, 1.0, 0.1)]),
+            ("timeouts_between", 1200, 18000, 14000, 0.1,
+             [(5000, "first message", 1.0, 0.1), (3000, "2nd", 1.0, 0.1), (20000, "the third and last one", 1.0, 0.1), (9000, None, 1.0, 0.1)]),
+            ("back_to_back", 1200, 18000, 14000, 1.0,
+             [(2048, "a", 1.0, 0.05), (0, "b", 1.0, 0.05), (100, "c", 1.0, 0.05), (7000, None, 1.0, 0.05)]),
+            ("quiet_and_loud_2400", 2400, 14000, 11000, 0.5,
+             [(9000, "loud one", 1.0, 0.1), (30000, "too quiet to open the gate", 0.3, 0.1), (12000, "loud again", 0.6, 0.1), (16000, None, 1.0, 0.1)]),
+            ("cut_open_at_end", 1200, 18000, 14000, 1.0,
+             [(4096, "complete", 1.0, 0.1), (6000, "this one is cut off by the end of the recording", 1.0, 0.1)]),
+            ("timeout_zero", 1200, 18000, 14000, 0.0, [(2048, "never heard", 1.0, 0.1), (8192, None, 1.0, 0.1)]),
+    ]:
+        parts = []
+        for lead, msg, gain, tt in segs:
+            parts.append(np.zeros(lead, np.int16))
+            if msg is not None:
+                parts.append((R.ref_save(msg, baud, tt).astype(np.float64) * gain).astype(np.int16))
+        s = np.concatenate(parts)
+        if name == "cut_open_at_end":
+            s = s[:len(s) - 9000]
+        calls = R.ref_receive_many(s, baud, a0, a1, timeout)
+        multi.append({"name": name, "baud": baud, "amp_start": a0, "amp_end": a1, "timeout": timeout,
+                      "segments": segs, "cut": 9000 if name == "cut_open_at_end" else 0, "n": int(len(s)),
+                      "sha256": hashlib.sha256(s.astype("<i2").tobytes()).hexdigest(),
+                      "calls": [{"timed_out": c["timed_out"], "exc": c["exc"], "reads_before": c["reads_before"],
+                                 "reads_after": c["reads_after"],
+                                 "ret_hex": c["ret"].hex() if isinstance(c["ret"], (bytes, bytearray)) else None,
+                                 "clock": c["clock"], "train_end": c["train_end"], "nbits": c["nbits"]} for c in calls]})
+    json.dump(multi, open(os.path.join(HERE, "gate_multi_cases.json"), "w"), indent=1)
+    for f in ("rx_cases.npz", "rx_cases.json", "tx_cases.npz", "tx_cases.json", "gate_cases.json", "gate_multi_cases.json"):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 

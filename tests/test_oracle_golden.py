@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import load_gate_golden, load_rx_golden, load_tx_golden
+from conftest import gate_multi_stream, load_gate_golden, load_gate_multi_golden, load_rx_golden, load_tx_golden
 from oracle import oracle as O
 
 RX = load_rx_golden()
@@ -87,3 +87,29 @@ def test_listen_gate_matches_reference_receive(g):
     else:
         # reads = 1 discarded + chunks examined before the timeout fired
         assert g["ret_hex"] == ""
+
+
+@pytest.mark.parametrize("g", load_gate_multi_golden(), ids=[g["name"] for g in load_gate_multi_golden()])
+def test_listen_gate_multi_matches_successive_reference_receives(g):
+    """Several transmissions in one recording: the oracle's walk equals successive receive() calls
+    of ONE reference Receiver (which keeps its stream open between calls, afskmodem.py:283)."""
+    s = gate_multi_stream(g, O.tx_frames)
+    calls = O.listen_gate_multi(s, g["amp_start"], g["amp_end"], int(g["timeout"] * 48000))
+    ref = g["calls"]
+    assert len(calls) >= len(ref)
+    for (rec, a, b), c in zip(calls, ref):
+        assert rec == (not c["timed_out"])
+        if not rec:
+            assert c["ret_hex"] == ""
+            continue
+        assert b // 2048 == c["reads_after"] and a // 2048 > c["reads_before"]
+        o = O.rx_decode(s[a:b], g["baud"], g["amp_end"])
+        assert o["data"].hex() == c["ret_hex"]
+        assert (o["clock"], o["train_end"], o["nbits"]) == (c["clock"], c["train_end"], c["nbits"])
+    # finite-recording convention: the only call the reference does not report (its stream.read
+    # would block) is a last recording still open when the samples run out
+    extra = calls[len(ref):]
+    assert len(extra) <= 1 and all(rec and b == (len(s) // 2048) * 2048 for rec, a, b in extra)
+    # the single-call gate is the first call of the walk
+    if calls:
+        assert O.listen_gate(s, g["amp_start"], g["amp_end"], int(g["timeout"] * 48000)) == calls[0]

@@ -298,14 +298,18 @@ class Receiver:
         self._log = Log("afskmodem.Receiver")
         self._cache = None                                       # (key, RxSession) of the last batch layout
 
-    def _session(self, offsets: np.ndarray, dev: int) -> RxSession:
+    def _session(self, offsets: np.ndarray, dev: int, baud=None, amp_end=None) -> RxSession:
         """Plan + device buffers are kept between calls with the same batch layout (like an FFT
         plan cache): repeated decode_batch calls then pay only H2D, kernels and D2H."""
-        key = (dev, self._baud, _as_int_threshold(self._amp_end), offsets.tobytes())
+        baud = self._baud if baud is None else np.ascontiguousarray(baud, dtype=np.int32)
+        amp_end = _as_int_threshold(self._amp_end) if amp_end is None else \
+            np.ceil(np.asarray(amp_end, dtype=np.float64)).astype(np.int32)
+        key = (dev, baud if np.isscalar(baud) else baud.tobytes(), amp_end if np.isscalar(amp_end) else amp_end.tobytes(),
+               offsets.tobytes())
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1]
         self.close()
-        s = RxSession(offsets, self._baud, _as_int_threshold(self._amp_end), dev)
+        s = RxSession(offsets, baud, amp_end, dev)
         self._cache = (key, s)
         return s
 
@@ -322,14 +326,16 @@ class Receiver:
             pass
 
     # -- batch API -------------------------------------------------------------------------
-    def decode_batch(self, samples, offsets=None, device: int | None = None) -> RxBatch:
+    def decode_batch(self, samples, offsets=None, device: int | None = None, baud_rate=None,
+                     amp_end_threshold=None) -> RxBatch:
         """Decode B captures.  ``samples``: list of int16 arrays, or one concatenated int16 array
-        with ``offsets`` (B+1, in samples).  Raises the reference's exceptions only through
-        ``to_python``; statuses < 0 mark captures on which ``load`` would raise."""
+        with ``offsets`` (B+1, in samples).  ``baud_rate`` / ``amp_end_threshold`` (arrays of B) override
+        this receiver's settings per capture for mixed corpora.  Raises the reference's exceptions
+        only through ``to_python``; statuses < 0 mark captures on which ``load`` would raise."""
         if offsets is None:
             samples, offsets = _concat(samples)
         dev = self._device if device is None else device
-        s = self._session(np.ascontiguousarray(offsets, dtype=np.int64), dev)
+        s = self._session(np.ascontiguousarray(offsets, dtype=np.int64), dev, baud_rate, amp_end_threshold)
         s.upload(samples)
         s.run()
         return s.download()

@@ -39,34 +39,61 @@ sys.path.insert(0, ROOT)
 BAUD = 1200
 PAYLOAD = 1024
 AMP_END = 14000
-# other BASELINE configs, for tuning runs only (the bench line of record is c2):
+# other BASELINE configs, for tuning runs and profiles/ (the bench line of record is c2):
 #   c3: 6000 baud stand-in for the reference-unsupported 9600, 16384 x 1 KB
 #   c4: 300 baud, 64 KB payloads, 64 captures of 146.8 M samples
-WORKLOADS = {"c2": (1200, 1024, 4096), "c3": (6000, 1024, 16384), "c4": (300, 65536, 64)}
+#   c5: mixed-baud corpus: 12500 captures per GPU (100k over 8 GPUs), baud in
+#       {300,600,1200,2400,4000,6000} + 1 % each of 4800 / 9600 (exception parity), payloads
+#       log-uniform 16 B - 4 KB, per-capture thresholds / gains / training times
+WORKLOADS = {"c2": (1200, 1024, 4096), "c3": (6000, 1024, 16384), "c4": (300, 65536, 64), "c5": (0, 0, 12500)}
 SIGMAS = np.array([0, 2000, 8000, 14000, 19000, 26000], dtype=np.float64)
 SIGMA_W = np.array([1, 2, 3, 2, 1, 1], dtype=np.float64) / 10.0
-CLEAN_N = 602400                 # frames Transmitter(1200).save writes for 1 KB
 WL = "c2"
 
 
 def set_workload(name, captures):
-    global BAUD, PAYLOAD, CLEAN_N, WL
+    global BAUD, PAYLOAD, WL
     WL = name
     BAUD, PAYLOAD, default_b = WORKLOADS[name]
-    CLEAN_N = (2 * int(BAUD * 0.5 / 2) + 4 + 14 * PAYLOAD) * (48000 // BAUD) + 4800
     return captures if captures else default_b
 
 
 def workload_name(B):
+    if WL == "c5":
+        return (f"c5: {B} mixed-baud captures (300-6000 baud + 1% each 4800/9600), payloads 16 B-4 KB log-uniform, "
+                "per-capture thresholds/gains/training times, AWGN mix")
     return f"{WL}: {B} x {BAUD}-baud captures, {PAYLOAD} B payload, AWGN mix, 25% lead silence"
 
 
-def capture_recipe(B, rank):
-    rng = np.random.default_rng([2, rank])
-    payloads = rng.integers(0, 256, size=(B, PAYLOAD), dtype=np.uint8)
-    lead = np.where(rng.random(B) < 0.25, rng.integers(0, 4000, B), 0).astype(np.int64)
-    sigma = rng.choice(SIGMAS, size=B, p=SIGMA_W)
-    return payloads, lead, sigma
+def corpus_spec(B, rank):
+    """Per-capture recipe of the workload, seeded by (config, rank)."""
+    if WL != "c5":
+        rng = np.random.default_rng([2, rank])
+        payloads = [p.tobytes() for p in rng.integers(0, 256, size=(B, PAYLOAD), dtype=np.uint8)]
+        lead = np.where(rng.random(B) < 0.25, rng.integers(0, 4000, B), 0).astype(np.int64)
+        sigma = rng.choice(SIGMAS, size=B, p=SIGMA_W)
+        one = np.ones(B)
+        return {"payloads": payloads, "lead": lead, "sigma": sigma, "gain": one, "tt": 0.5 * one,
+                "baud_tx": np.full(B, BAUD, np.int32), "baud_rx": np.full(B, BAUD, np.int32),
+                "amp_end": np.full(B, AMP_END, np.int32)}
+    rng = np.random.default_rng([5, rank])
+    baud_rx = rng.choice(np.array([300, 600, 1200, 2400, 4000, 6000, 4800, 9600], np.int32), size=B,
+                         p=[0.1633, 0.1633, 0.1634, 0.1633, 0.1633, 0.1634, 0.01, 0.01])
+    baud_tx = np.where(baud_rx == 9600, 6000, baud_rx).astype(np.int32)   # nothing can synthesize 9600 (SURVEY F1)
+    plen = np.exp(rng.uniform(np.log(16), np.log(4096), B)).astype(np.int64)
+    payloads = [rng.integers(0, 256, int(n), dtype=np.uint8).tobytes() for n in plen]
+    pair = rng.integers(0, 3, B)
+    amp_end = np.array([14000, 11000, 8000], np.int32)[pair]
+    gain = np.where(pair == 0, rng.choice([1.0, 0.7], B), np.where(pair == 1, rng.choice([1.0, 0.7, 0.45], B),
+                                                                    rng.choice([1.0, 0.7, 0.45, 0.3], B)))
+    return {"payloads": payloads, "lead": np.where(rng.random(B) < 0.25, rng.integers(0, 4000, B), 0).astype(np.int64),
+            "sigma": rng.choice(SIGMAS, size=B, p=SIGMA_W), "gain": gain, "tt": rng.choice([0.5, 1.5, 0.1, 0.02], B),
+            "baud_tx": baud_tx, "baud_rx": baud_rx.astype(np.int32), "amp_end": amp_end}
+
+
+def expected_status_negative(spec):
+    """captures on which the reference raises (9600: constructor; 4800: load on >= 4096 frames)"""
+    return (spec["baud_rx"] == 9600) | (spec["baud_rx"] == 4800)
 
 
 class ClockSampler(threading.Thread):
@@ -106,63 +133,71 @@ class ClockSampler(threading.Thread):
 
 
 def build_batch_on_gpu(B, rank, device):
-    """Synthesizes the batch with the GPU transmitter, then lead silence + AWGN with torch (plumbing)."""
+    """Synthesizes the batch with the GPU transmitter, then lead silence, gain and AWGN with torch
+    (plumbing).  Returns (samples on the device, offsets, spec)."""
+    import ctypes
+
     import torch
 
     import afskmodem_b200 as A
-    payloads, lead, sigma = capture_recipe(B, rank)
-    ts = int(BAUD * 0.5 / 2)
-    import ctypes
+    spec = corpus_spec(B, rank)
+    ts = [int(b * t / 2) for b, t in zip(spec["baud_tx"], spec["tt"])]             # afskmodem.py:438
     dev = torch.device("cuda", device)
-    tx = A.TxSession([p.tobytes() for p in payloads], BAUD, ts, device)
+    tx = A.TxSession(spec["payloads"], spec["baud_tx"], ts, device)
     tx.upload()
-    assert int(tx.out_len[0]) == CLEAN_N
     # synthesize straight into a torch-owned buffer (caller-owned device pointer through the C ABI)
     clean = torch.empty(int(tx.out_off[-1]) + 64, dtype=torch.int16, device=dev)
     A._cabi.check(A._cabi.lib().afsk_tx_synth(tx.plan, ctypes.c_void_p(tx.d_pay.ptr), ctypes.c_void_p(clean.data_ptr()),
                                               None))
     A._cabi.stream_sync(device)
-    lens = lead + CLEAN_N
+    lead, sigma, gain = spec["lead"], spec["sigma"], spec["gain"]
+    clean_n = tx.out_len.astype(np.int64)
+    lens = lead + clean_n
     offsets = np.zeros(B + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
     total = int(offsets[-1])
     samples = torch.zeros(total + 64, dtype=torch.int16, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    chunk = max(1, min(128, (1 << 27) // CLEAN_N))
-    for c0 in range(0, B, chunk):
-        c1 = min(B, c0 + chunk)
+    c0 = 0
+    while c0 < B:
+        c1 = c0 + 1
+        while c1 < B and c1 - c0 < 256 and offsets[c1 + 1] - offsets[c0] <= (1 << 27):
+            c1 += 1
         for c in range(c0, c1):
             o = int(offsets[c]) + int(lead[c])
-            samples[o:o + CLEAN_N] = clean[int(tx.out_off[c]):int(tx.out_off[c]) + CLEAN_N]
+            samples[o:o + int(clean_n[c])] = clean[int(tx.out_off[c]):int(tx.out_off[c]) + int(clean_n[c])]
         a, b = int(offsets[c0]), int(offsets[c1])
-        sig = torch.repeat_interleave(torch.as_tensor(sigma[c0:c1], dtype=torch.float32, device=dev),
-                                      torch.as_tensor(lens[c0:c1], device=dev))
+        ln = torch.as_tensor(lens[c0:c1], device=dev)
+        sig = torch.repeat_interleave(torch.as_tensor(sigma[c0:c1], dtype=torch.float32, device=dev), ln)
+        gn = torch.repeat_interleave(torch.as_tensor(gain[c0:c1], dtype=torch.float32, device=dev), ln)
         noise = torch.round(torch.randn(b - a, generator=gen, device=dev, dtype=torch.float32) * sig)
-        samples[a:b] = torch.clamp(samples[a:b].to(torch.float32) + noise, -32768, 32767).to(torch.int16)
-        del sig, noise
+        samples[a:b] = torch.clamp(torch.trunc(samples[a:b].to(torch.float32) * gn) + noise, -32768, 32767).to(torch.int16)
+        del sig, gn, noise
+        c0 = c1
     tx.close()
     del clean
     torch.cuda.synchronize(dev)
-    return samples, offsets, payloads, sigma, lead
+    return samples, offsets, spec
 
 
 def host_sample_batch(B, rank=0):
     """Same recipe on the host (oracle transmitter + numpy AWGN) for the reference arm."""
     from oracle import oracle as O
-    payloads, lead, sigma = capture_recipe(B, rank)
+    spec = corpus_spec(B, rank)
     rng = np.random.default_rng([3, rank])
     caps = []
     for c in range(B):
-        fr = O.tx_frames(payloads[c].tobytes(), BAUD, 0.5)
-        x = np.concatenate([np.zeros(int(lead[c]), np.int16), fr]).astype(np.float32)
-        if sigma[c] > 0:
-            x += np.round(rng.normal(0.0, sigma[c], len(x))).astype(np.float32)
+        fr = O.tx_frames(spec["payloads"][c], int(spec["baud_tx"][c]), float(spec["tt"][c]))
+        x = np.concatenate([np.zeros(int(spec["lead"][c]), np.int16), fr]).astype(np.float32)
+        x = np.trunc(x * np.float32(spec["gain"][c]))
+        if spec["sigma"][c] > 0:
+            x += np.round(rng.normal(0.0, spec["sigma"][c], len(x))).astype(np.float32)
         caps.append(np.clip(x, -32768, 32767).astype(np.int16))
     lens = np.array([len(c) for c in caps], dtype=np.int64)
     off = np.zeros(B + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
-    return np.concatenate(caps), off, payloads
+    return np.concatenate(caps), off, spec
 
 
 def run_reference(args):
@@ -174,23 +209,23 @@ def run_reference(args):
     O.build()
     cores = os.cpu_count() or 1
     nsample = 256
-    samples, off, payloads = host_sample_batch(nsample)
+    samples, off, spec = host_sample_batch(nsample)
     for _ in range(max(args.warmup, 1)):
-        O.rx_decode_batch(samples, off, BAUD, AMP_END, threads=cores)
+        O.rx_decode_batch(samples, off, spec["baud_rx"], spec["amp_end"], threads=cores)
     t0 = time.perf_counter()
     nbytes = 0
     for _ in range(args.steps):
-        datas, _ = O.rx_decode_batch(samples, off, BAUD, AMP_END, threads=cores)
+        datas, _ = O.rx_decode_batch(samples, off, spec["baud_rx"], spec["amp_end"], threads=cores)
         nbytes += sum(len(d) for d in datas)
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1000
     val = float(off[-1]) / (ms / 1000) / 1e6
-    sample = f"{nsample} captures of the c2 recipe ({int(off[-1])} samples) per step, C port of afskmodem.py on {cores} threads"
+    sample = f"{nsample} captures of the {WL} recipe ({int(off[-1])} samples) per step, C port of afskmodem.py on {cores} threads"
     line = {"impl": "reference", "metric": "decoded Msamples/s", "value": val, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16",
             "data": "synthetic", "mbit_s": 8 * nbytes / dt / 1e6,
-            "config": {"workload": workload_name(4096), "sample": sample},
+            "config": {"workload": workload_name(args.captures), "sample": sample},
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -232,9 +267,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.captures
 
-    samples, offsets, payloads, sigma, lead = build_batch_on_gpu(B, rank, local)
+    samples, offsets, spec = build_batch_on_gpu(B, rank, local)
+    payloads, sigma = spec["payloads"], spec["sigma"]
     total = int(offsets[-1])
-    sess = A.RxSession(offsets, BAUD, AMP_END, local)
+    sess = A.RxSession(offsets, spec["baud_rx"], spec["amp_end"], local)
     sess.bind(samples.data_ptr())
     stream = torch.cuda.current_stream(dev).cuda_stream
 
@@ -248,13 +284,16 @@ def main():
         picks = sorted(set([0, 1, 2, 3, B // 2, B - 1][:6 if WL != "c4" else 2] + [int(np.argmax(sigma == s)) for s in SIGMAS if (sigma == s).any()]))
         for c in picks:
             x = samples[int(offsets[c]):int(offsets[c + 1])].cpu().numpy()
-            o = O.rx_decode(x, BAUD, AMP_END)
+            o = O.rx_decode(x, int(spec["baud_rx"][c]), int(spec["amp_end"][c]))
             got = (int(batch.status[c]), int(batch.clock[c]), int(batch.train_end[c]), int(batch.nbits[c]), batch.payload(c))
             want = (o["status"], o["clock"], o["train_end"], o["nbits"], o["data"])
             if got != want:
                 raise SystemExit(f"PARITY FAILURE on capture {c}: {got[:4]} != {want[:4]}")
             parity_checked += 1
-    exact = int(sum(batch.payload(c) == payloads[c].tobytes() for c in range(B)))
+    exact = int(sum(batch.payload(c) == payloads[c] for c in range(B)))
+    raising = int((batch.status < 0).sum())
+    if raising != int(expected_status_negative(spec).sum()) and WL == "c5":
+        raise SystemExit(f"PARITY FAILURE: {raising} captures flagged as raising, expected {int(expected_status_negative(spec).sum())}")
 
     def barrier():
         if world > 1:
@@ -300,13 +339,14 @@ def main():
     if not args.no_e2e:
         pin = _cabi.PinnedArray((total + 64,), np.int16)
         pin.array[:total] = samples[:total].cpu().numpy()
-        rx = A.Receiver(BAUD, 18000, AMP_END, device=local)
-        rx.decode_batch(pin.array, offsets)            # warm-up (first call pays context / allocator set-up)
+        rx = A.Receiver(1200, 18000, AMP_END, device=local)
+        kw = {"baud_rate": spec["baud_rx"], "amp_end_threshold": spec["amp_end"]}     # per-capture settings
+        rx.decode_batch(pin.array, offsets, **kw)      # warm-up (first call pays context / allocator set-up)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(args.e2e_steps):
-            hb = rx.decode_batch(pin.array, offsets)
+            hb = rx.decode_batch(pin.array, offsets, **kw)
         s1.record()
         barrier()
         te = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
@@ -316,7 +356,8 @@ def main():
         assert hb.total_payload_bytes() == decoded_bytes
         e2e = {"value": all_samples / (e2e_ms / 1000) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": total * 2, "d2h_bytes_per_step": int(32 * B + hb.out_off[-1]),
-               "api": "Receiver.decode_batch(pinned int16 samples, offsets)", "steps": args.e2e_steps}
+               "api": "Receiver.decode_batch(pinned int16 samples, offsets, baud_rate=[...], amp_end_threshold=[...])",
+               "steps": args.e2e_steps}
         pin.close()
 
     if rank != 0:
@@ -353,11 +394,13 @@ def main():
         cores = os.cpu_count() or 1
         nc = min(B, args.cpu_captures)
         hs = samples[:int(offsets[nc])].cpu().numpy()
-        O.rx_decode_batch(hs[:int(offsets[min(nc, 64)])], offsets[:min(nc, 64) + 1], BAUD, AMP_END, threads=cores)
+        w = min(nc, 64)
+        O.rx_decode_batch(hs[:int(offsets[w])], offsets[:w + 1], spec["baud_rx"][:w], spec["amp_end"][:w], threads=cores)
         t0 = time.perf_counter()
-        datas, _ = O.rx_decode_batch(hs, offsets[:nc + 1], BAUD, AMP_END, threads=cores)
+        datas, ores = O.rx_decode_batch(hs, offsets[:nc + 1], spec["baud_rx"][:nc], spec["amp_end"][:nc], threads=cores)
         dt = time.perf_counter() - t0
         assert datas == [batch.payload(c) for c in range(nc)], "GPU payloads != oracle payloads on the CPU sample"
+        assert [ores[c].status for c in range(nc)] == [int(v) for v in batch.status[:nc]], "GPU statuses != oracle statuses"
         parity_checked = max(parity_checked, nc)
         cpu = {"value": float(offsets[nc]) / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
                "sample": f"first {nc} captures of the workload ({int(offsets[nc])} samples), C port of afskmodem.py "
@@ -368,8 +411,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
             "mbit_s": mbit,
             "config": {"workload": workload_name(B), "captures_per_gpu": B, "samples_per_gpu": total,
-                       "baud": BAUD, "payload_bytes": PAYLOAD, "l2_policy": "inputs (4.9 GB/GPU) larger than L2; no flush",
-                       "payloads_exact": exact, "parity_checked_vs_oracle": parity_checked},
+                       "baud": BAUD or "mixed", "payload_bytes": PAYLOAD or "16-4096",
+                       "l2_policy": f"inputs ({2 * total / 1e9:.1f} GB/GPU) larger than L2; no flush",
+                       "payloads_exact": exact, "captures_raising_like_reference": raising,
+                       "parity_checked_vs_oracle": parity_checked},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * sess.launches,
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))

@@ -262,6 +262,34 @@ def test_ranges_plan_equals_adjacent_plan():
     s.close()
 
 
+def test_mixed_corpus_per_capture_settings():
+    """BASELINE config #5 in miniature: one batch mixing bauds (including 4800, where load raises, and
+    9600, where the constructor does), per-capture amp_end thresholds with matching gains, training
+    times, payload sizes and noise — through Receiver.decode_batch's per-capture overrides."""
+    rng = np.random.default_rng(55)
+    B = 96
+    baud_rx = rng.choice([300, 600, 1200, 2400, 4000, 6000, 4800, 9600], size=B, p=[.15, .15, .15, .15, .15, .15, .05, .05])
+    caps, thr = [], []
+    for c in range(B):
+        btx = 6000 if baud_rx[c] == 9600 else int(baud_rx[c])
+        pl = rng.integers(0, 256, int(np.exp(rng.uniform(np.log(16), np.log(600)))), dtype=np.uint8).tobytes()
+        pair = int(rng.integers(0, 3))
+        thr.append([14000, 11000, 8000][pair])
+        gain = float(rng.choice([[1.0, 0.7], [1.0, 0.7, 0.45], [1.0, 0.7, 0.45, 0.3]][pair]))
+        fr = O.tx_frames(pl, btx, float(rng.choice([0.5, 1.5, 0.1, 0.02])))
+        caps.append(_impair(fr, rng, lead=int(rng.integers(0, 4000)) if c % 4 == 0 else 0, gain=gain,
+                            sigma=float(rng.choice([0, 2000, 8000, 14000, 19000, 26000]))))
+    r = A.Receiver(1200)
+    b = r.decode_batch(caps, baud_rate=baud_rx, amp_end_threshold=thr)
+    _check_against_oracle(b, caps, baud_rx, thr)
+    assert ((b.status < 0) == ((baud_rx == 9600) | (baud_rx == 4800))).all()
+    i9600, i4800 = int(np.argmax(baud_rx == 9600)), int(np.argmax(baud_rx == 4800))
+    with pytest.raises(Exception, match="Invalid baud rate."):
+        r.to_python(b, i9600)
+    with pytest.raises(Exception, match="Comparing two waveforms of different lengths."):
+        r.to_python(b, i4800)
+
+
 def test_full_size_roundtrip_property():
     """BASELINE config #2 shape (1200 baud, 1 KB payloads, 602,400 samples each) at B=256:
     GPU synth -> AWGN (sigma=8000) -> GPU decode returns every payload; the clean batch returns

@@ -22,7 +22,7 @@ def main():
     wl = sys.argv[1]
     variants = sys.argv[2:] or [""]
     B = bench.set_workload(wl, 0)
-    samples, offsets, *_ = bench.build_batch_on_gpu(B, 0, 0)
+    samples, offsets, spec = bench.build_batch_on_gpu(B, 0, 0)
     total = int(offsets[-1])
     stream = torch.cuda.current_stream().cuda_stream
     knobs = sorted({kv.split("=")[0] for v in variants for kv in v.split(",") if kv})
@@ -38,7 +38,7 @@ def main():
     sessions = []
     for v in variants:
         setenv(v)
-        s = A.RxSession(offsets, bench.BAUD, bench.AMP_END, 0)
+        s = A.RxSession(offsets, spec["baud_rx"], spec["amp_end"], 0)
         s.bind(samples.data_ptr())
         sessions.append(s)
     times = [[] for _ in variants]

@@ -26,6 +26,7 @@ SYMBOLS = [
     "afsk_rx_plan_launches", "afsk_rx_plan_set_timing", "afsk_rx_plan_demod_time", "afsk_rx_decode", "afsk_rx_plan_planes", "afsk_rx_decode_host",
     "afsk_rx_out_capacity", "afsk_rx_gate", "afsk_rx_gate_multi", "afsk_tx_num_samples", "afsk_tx_plan_create",
     "afsk_tx_plan_destroy", "afsk_tx_plan_out_offsets", "afsk_tx_synth", "afsk_tx_synth_host",
+    "afsk_wav_probe", "afsk_wav_load", "afsk_wav_save",
 ]
 
 
@@ -94,6 +95,10 @@ def lib():
     L.afsk_tx_plan_out_offsets.argtypes = [vp, C.POINTER(i64p), C.POINTER(i64p)]
     L.afsk_tx_synth.argtypes = [vp, vp, vp, vp]
     L.afsk_tx_synth_host.argtypes = [C.c_int, u8p, i64p, C.c_int, i32p, i64p, i16p, i64p]
+    cpp = C.POINTER(C.c_char_p)
+    L.afsk_wav_probe.argtypes = [cpp, C.c_int, C.c_int, i64p, i64p, i32p]
+    L.afsk_wav_load.argtypes = [cpp, C.c_int, C.c_int, i64p, i64p, i64p, vp, C.c_int, vp, C.c_int64, vp, i32p]
+    L.afsk_wav_save.argtypes = [cpp, C.c_int, C.c_int, vp, i64p, i64p, i32p]
     _lib = L
     return L
 
@@ -167,6 +172,13 @@ class PinnedArray:
             self._ptr = None
 
     __del__ = close
+
+
+def c_paths(filenames):
+    """list of str/bytes/PathLike -> (char*[n], keep-alive list)"""
+    enc = [os.fsencode(f) for f in filenames]
+    arr = (C.c_char_p * max(len(enc), 1))(*enc)
+    return arr, enc
 
 
 def stream_sync(device: int, stream=None):

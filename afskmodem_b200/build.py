@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libafsk_b200.so")
-SOURCES = ["afsk_api.cu", "afsk_rx.cu", "afsk_tx.cu"]
+SOURCES = ["afsk_api.cu", "afsk_rx.cu", "afsk_tx.cu", "afsk_io.cu"]
 HEADERS = [os.path.join(CSRC, "afsk_common.cuh"), os.path.join(HERE, "..", "include", "afsk_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

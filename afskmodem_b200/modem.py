@@ -285,6 +285,69 @@ def read_wav_frames(filename: str) -> np.ndarray:
     return np.frombuffer(raw, dtype="<i2", count=len(raw) // 2)
 
 
+class WavBatch:
+    """Frames of many wav files in ONE pinned int16 buffer (CSR offsets), read by the library's host
+    thread pool — SoundInput.loadFromFile (afskmodem.py:213-217) for a batch.  Files the native
+    reader does not vouch for (status != 0) go through CPython's ``wave`` module exactly like the
+    reference, so whatever ``wave.open`` / ``readframes`` raises there is kept per file in ``errors``."""
+
+    def __init__(self, filenames, threads: int = 0):
+        L = _cabi.lib()
+        self.filenames = list(filenames)
+        n = len(self.filenames)
+        self._paths, self._keep = _cabi.c_paths(self.filenames)
+        self.nsamples = np.zeros(max(n, 1), dtype=np.int64)
+        self.data_pos = np.zeros(max(n, 1), dtype=np.int64)
+        self.status = np.zeros(max(n, 1), dtype=np.int32)
+        self.threads = threads
+        _cabi.check(L.afsk_wav_probe(self._paths, n, threads, _cabi.ptr(self.nsamples, C.c_int64),
+                                     _cabi.ptr(self.data_pos, C.c_int64), _cabi.ptr(self.status, C.c_int32)))
+        self.errors: dict[int, Exception] = {}
+        self.fallback: dict[int, np.ndarray] = {}
+        for i in np.nonzero(self.status[:n])[0]:
+            try:
+                self.fallback[int(i)] = read_wav_frames(self.filenames[i])
+                self.nsamples[i] = len(self.fallback[int(i)])
+            except Exception as e:  # noqa: BLE001 - what the reference's wave.open raises for this file
+                self.errors[int(i)] = e
+                self.nsamples[i] = 0
+        self.offsets = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(self.nsamples[:n], out=self.offsets[1:])
+        self.total = int(self.offsets[-1])
+        self.pinned = self.array = None
+
+    def __len__(self) -> int:
+        return len(self.filenames)
+
+    def read(self, pinned=None, device: int = 0, d_samples: int | None = None, stream=None):
+        """Reads every file into ``pinned`` (a ``_cabi.PinnedArray``, allocated when None or too small;
+        a plain numpy int16 array also works, for hosts without a GPU); with ``d_samples`` (device
+        pointer) each finished span is copied to the GPU while later files are still being read."""
+        n = len(self)
+        arr = pinned if isinstance(pinned, np.ndarray) else (pinned.array if pinned is not None else None)
+        if arr is None or arr.size < self.total + 64:
+            pinned = _cabi.PinnedArray((self.total + 64,), np.int16)
+            arr = pinned.array
+        self.pinned, self.array = pinned, arr
+        for i, fr in self.fallback.items():
+            arr[self.offsets[i]:self.offsets[i + 1]] = fr
+        ns = self.nsamples.copy()
+        for i in list(self.fallback) + list(self.errors):
+            ns[i] = 0                                   # not read natively (already in place / unreadable)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        _cabi.check(_cabi.lib().afsk_wav_load(self._paths, n, self.threads, _cabi.ptr(self.data_pos, C.c_int64),
+                                              _cabi.ptr(ns, C.c_int64), _cabi.ptr(self.offsets, C.c_int64),
+                                              C.c_void_p(arr.ctypes.data), device,
+                                              C.c_void_p(d_samples) if d_samples else None, 0,
+                                              C.c_void_p(stream or 0), _cabi.ptr(st, C.c_int32)))
+        for i in np.nonzero(st[:n])[0]:
+            self.errors[int(i)] = OSError(f"cannot read {self.filenames[i]!r}")
+        return arr[:self.total]
+
+    def frames(self, i: int) -> np.ndarray:
+        return self.array[self.offsets[i]:self.offsets[i + 1]]
+
+
 class Receiver:
     """Receiver(baud_rate, amp_start_threshold, amp_end_threshold) — afskmodem.py:274-430."""
 
@@ -318,6 +381,9 @@ class Receiver:
         if getattr(self, "_cache", None) is not None:
             self._cache[1].close()
             self._cache = None
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
+            self._pinned = None
 
     def __del__(self):
         try:
@@ -367,15 +433,27 @@ class Receiver:
             return data.decode("utf-8")                                            # :428-429
         return data
 
-    def load_batch(self, filenames, string: bool = True, errors: str = "raise"):
-        """``load`` over many files in one GPU batch.  errors="return" puts the exception object in
-        the list instead of raising at the first failing capture."""
-        caps = [read_wav_frames(f) for f in filenames]
-        batch = self.decode_batch(caps)
+    def load_batch(self, filenames, string: bool = True, errors: str = "raise", threads: int = 0, log: bool = True):
+        """``load`` over many files in one GPU batch: the library's host threads read the wav files
+        into one pinned buffer while finished spans stream to the GPU, then one decode.
+        errors="return" puts the exception object in the list instead of raising at the first
+        failing file."""
+        wb = WavBatch(filenames, threads)
+        dev = self._device
+        s = self._session(wb.offsets, dev)
+        if s.d_samples is None:
+            s.d_samples = DeviceBuffer(dev, (wb.total * 2 + 15) // 16 * 16 + 16)
+        s._ext_ptr = None
+        wb.read(getattr(self, "_pinned", None), dev, s.d_samples.ptr)
+        self._pinned = wb.pinned                                 # kept (grow-only) for the next batch
+        s.run()
+        batch = s.download()
         out = []
-        for i in range(len(caps)):
+        for i in range(len(wb)):
             try:
-                out.append(self.to_python(batch, i, string))
+                if i in wb.errors:
+                    raise wb.errors[i]
+                out.append(self.to_python(batch, i, string, log))
             except Exception as e:  # noqa: BLE001 - mirrors whatever load raises
                 if errors == "raise":
                     raise
@@ -598,6 +676,25 @@ def write_wav_frames(filename: str, frames: np.ndarray) -> None:
         f.writeframes(np.ascontiguousarray(frames, dtype="<i2").tobytes())
 
 
+def write_wav_batch(filenames, samples: np.ndarray, starts, lengths, threads: int = 0) -> None:
+    """SoundOutput.writeToFile (afskmodem.py:256-263) for many files: file i = samples[starts[i] : starts[i] + lengths[i]]."""
+    filenames = list(filenames)
+    n = len(filenames)
+    samples = np.ascontiguousarray(samples, dtype="<i2")
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    assert len(starts) >= n and len(lengths) >= n
+    paths, _keep = _cabi.c_paths(filenames)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    _cabi.check(_cabi.lib().afsk_wav_save(paths, n, threads, C.c_void_p(samples.ctypes.data), _cabi.ptr(starts, C.c_int64),
+                                          _cabi.ptr(lengths, C.c_int64), _cabi.ptr(st, C.c_int32)))
+    for i in np.nonzero(st[:n])[0]:
+        if st[i] == 2:
+            write_wav_frames(filenames[i], samples[starts[i]:starts[i] + lengths[i]])   # raises like wave does
+        else:
+            raise OSError(f"cannot write {filenames[i]!r}")
+
+
 class Transmitter:
     """Transmitter(baud_rate, training_time) — afskmodem.py:436-484."""
 
@@ -625,10 +722,11 @@ class Transmitter:
         finally:
             s.close()
 
-    def save_batch(self, payloads, filenames) -> None:
+    def save_batch(self, payloads, filenames, threads: int = 0) -> None:
+        """``save`` for many payloads: one synthesis on the GPU, files written by the library's host
+        threads (byte-identical to the reference's wave output)."""
         batch = self.encode_batch(payloads)
-        for i, fn in enumerate(filenames):
-            write_wav_frames(fn, batch.frames(i))
+        write_wav_batch(filenames, batch.samples, batch.out_off[:-1], batch.out_len, threads)
 
     def save(self, data: str | bytes, filename: str):
         """Transmits the given data, saving the resulting audio to a .wav file — afskmodem.py:481-484."""

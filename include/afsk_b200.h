@@ -172,6 +172,31 @@ int afsk_tx_synth_host(int device, const uint8_t *h_payload, const int64_t *h_pa
                        const int32_t *h_baud, const int64_t *h_ts_cycles, int16_t *h_out,
                        const int64_t *h_out_off);
 
+/* ---------------------------------------------------------------- wav files ------------ */
+/*
+ * Host ingest / egress for batches of files (one pool of host threads; threads <= 0: all cores).
+ * Replaces SoundInput.loadFromFile + __convertFrames (afskmodem.py:201-205, 213-217: every frame byte
+ * of the data chunk, paired little-endian signed whatever the header says about channels or sample
+ * width) and SoundOutput.writeToFile (afskmodem.py:256-263: 1 channel / 2 bytes / 48000 Hz).
+ * Per-file status: AFSK_WAV_OK, or a reason to hand the file to CPython's wave module instead
+ * (which then raises exactly what the reference raises).
+ */
+#define AFSK_WAV_OK 0
+#define AFSK_WAV_E_OPEN 1      /* cannot open / read / write the file                     */
+#define AFSK_WAV_E_FORMAT 2    /* not plain RIFF/WAVE PCM with fmt before data            */
+/* samples (= data bytes / 2) and file position of the first frame byte of each file */
+int afsk_wav_probe(const char *const *paths, int n, int threads, int64_t *h_nsamples, int64_t *h_data_pos,
+                   int32_t *h_status);
+/* reads file i's samples into h_dst[h_offsets[i] ...] (pinned memory recommended).  With d_dst != NULL,
+ * spans of about span_samples consecutive samples are copied to d_dst (same offsets) on `stream` as
+ * soon as their files are in memory, so that reading overlaps the PCIe transfer. */
+int afsk_wav_load(const char *const *paths, int n, int threads, const int64_t *h_data_pos, const int64_t *h_nsamples,
+                  const int64_t *h_offsets, int16_t *h_dst, int device, int16_t *d_dst, int64_t span_samples,
+                  void *stream, int32_t *h_status);
+/* writes h_src[h_start[i] .. + h_len[i]) as file i, byte-identical to the reference's writeToFile */
+int afsk_wav_save(const char *const *paths, int n, int threads, const int16_t *h_src, const int64_t *h_start,
+                  const int64_t *h_len, int32_t *h_status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -290,6 +290,39 @@ def test_mixed_corpus_per_capture_settings():
         r.to_python(b, i4800)
 
 
+def test_save_batch_load_batch_files(tmp_path):
+    """Transmitter.save_batch -> wav files -> Receiver.load_batch (native threaded ingest into pinned
+    memory, spans streamed to the GPU while later files are read): same values as per-file load()."""
+    rng = np.random.default_rng(77)
+    n = 40
+    msgs = ["Hello World!", "Héellóo World!"] + [bytes(rng.integers(32, 127, int(rng.integers(1, 400)), dtype=np.uint8)).decode()
+                                                   for _ in range(n - 2)]
+    paths = [str(tmp_path / f"m{i}.wav") for i in range(n)]
+    t = A.Transmitter(1200, 0.1)
+    t.save_batch(msgs, paths)
+    for i in (0, 1, 7):
+        assert np.array_equal(A.read_wav_frames(paths[i]), O.tx_frames(msgs[i].encode("utf-8"), 1200, 0.1))
+    r = A.Receiver(1200)
+    assert r.load_batch(paths) == msgs
+    assert r.load_batch(paths, string=False) == [m.encode("utf-8") for m in msgs]       # cached plan + pinned buffer
+    assert [r.load(p) for p in paths[:3]] == msgs[:3]
+    # a file the wave module rejects, a missing file, a too-short capture and an undecodable one
+    bad = str(tmp_path / "bad.wav")
+    open(bad, "wb").write(b"RIFF\x04\x00\x00\x00WAVX")
+    short = str(tmp_path / "short.wav")
+    A.write_wav_frames(short, np.zeros(100, np.int16))
+    noise = str(tmp_path / "noise.wav")
+    A.write_wav_frames(noise, rng.integers(-32768, 32768, 60000, dtype=np.int16))
+    mixed = [paths[0], bad, str(tmp_path / "missing.wav"), short, noise, paths[1]]
+    got = r.load_batch(mixed, string=False, errors="return")
+    assert got[0] == msgs[0].encode() and got[5] == msgs[1].encode("utf-8") and got[3] == b""
+    assert type(got[1]).__name__ == "Error" and isinstance(got[2], FileNotFoundError)
+    assert got[4] == O.rx_decode(A.read_wav_frames(noise), 1200, 14000)["data"]
+    with pytest.raises(Exception):
+        r.load_batch(mixed)
+    r.close()
+
+
 def test_full_size_roundtrip_property():
     """BASELINE config #2 shape (1200 baud, 1 KB payloads, 602,400 samples each) at B=256:
     GPU synth -> AWGN (sigma=8000) -> GPU decode returns every payload; the clean batch returns

@@ -788,6 +788,140 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodPar
     }
 }
 
+// ------------------------------------------------------------------------ k_demod_shift ----
+// Short windows that are a multiple of 4 but not of 8 samples (bf = 12, 20: 4000 / 2400 baud).  One
+// thread decodes kWpt consecutive windows (kBf * kWpt samples, a multiple of 8).  A window boundary
+// then falls in the middle of a 16-byte vector, so the rotate-in-place trick of k_demod_small does
+// not apply; instead the tile's alignment e (0..7, uniform over the tile) selects one of eight
+// fully unrolled bodies in which the thread's words are picked at compile-time positions (even e:
+// plain register renaming; odd e: one PRMT per word to splice the two half-words).  Every group of
+// 4 samples lies inside one window (kBf % 4 == 0) and its +/-1 template weights are immediates.
+__host__ __device__ constexpr uint32_t tone_weights4(int bf, int pos, bool space)
+{
+    // signed-byte weights of window samples pos .. pos+3: mark + - + - per quarter, space + + - -
+    uint32_t w = 0;
+    for (int s = 0; s < 4; s++) {
+        const int qd = (pos + s) / (bf / 4);
+        const bool neg = space ? (qd & 2) != 0 : (qd & 1) != 0;
+        w |= (neg ? 0xFFu : 0x01u) << (8 * s);
+    }
+    return w;
+}
+
+template <int kBf, int kWpt, int kE>
+__device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int thr_bf, int nvalid, uint32_t &bits,
+                                             uint32_t &quiet)
+{
+    constexpr int kV = kBf * kWpt / 8;
+    uint32_t W[4 * (kV + 1)];
+#pragma unroll
+    for (int i = 0; i <= kV; i++) {
+        if (i < kV || kE > 0) {                      // an aligned tile never touches the extra vector
+            const uint4 v = dp[i];
+            W[4 * i] = v.x; W[4 * i + 1] = v.y; W[4 * i + 2] = v.z; W[4 * i + 3] = v.w;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < kWpt; w++) {
+        int accM = 0, accS = 0, accA = 0;
+#pragma unroll
+        for (int b = 0; b < kBf / 4; b++) {
+            const int pos = kE + w * kBf + 4 * b;    // first sample of the group in the loaded words
+            uint32_t a0, a1;
+            if ((kE & 1) == 0) {
+                a0 = W[pos / 2]; a1 = W[pos / 2 + 1];
+            } else {
+                a0 = prmt(W[(pos - 1) / 2], W[(pos + 1) / 2], 0x5432u);
+                a1 = prmt(W[(pos + 1) / 2], W[(pos + 3) / 2], 0x5432u);
+            }
+            accum4_full(a0, a1, tone_weights4(kBf, 4 * b, false), tone_weights4(kBf, 4 * b, true), k512, accM, accS, accA);
+        }
+        // acc = 256 * T.n + T.c with |T.c| <= kBf <= 127: decide as in k_demod
+        const int Um = (int)((unsigned)accM << 24) >> 24, Us = (int)((unsigned)accS << 24) >> 24;
+        const int du = Um - Us;
+        bool b1 = du > 0;
+        if (du == 0) {
+            const int Nm = (accM - Um) >> 8, Ns = (accS - Us) >> 8;
+            if (Ns > Nm) {
+                const int M2 = 65535 * kBf - 65534 * Um + 2 * Nm;
+                const int S2 = M2 + 2 * (Ns - Nm);
+                b1 = (S2 - M2 >= 2 * kBf) || (M2 < (S2 / (2 * kBf)) * (2 * kBf));
+            }
+        }
+        const bool valid = w < nvalid;
+        bits |= (uint32_t)(valid && b1) << w;
+        quiet |= (uint32_t)(valid && (accA < thr_bf)) << w;
+    }
+}
+
+template <int kBf, int kWpt>
+__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodParams p)
+{
+    static_assert(kBf % 4 == 0 && (kBf * kWpt) % 8 == 0 && 32 % kWpt == 0, "segment must be whole vectors");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.stages;
+    uint8_t *stage_base = smem;
+    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + (size_t)S * p.stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
+    uint64_t *empty = full + kMaxStages;
+    constexpr int kSeg = kBf * kWpt, kLanesPerWord = 32 / kWpt;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
+    if (ntile <= 0) return;
+    if (warp == kConsumerThreads / 32) {
+        demod_produce(p, ntile, stage_base, meta, full, empty);
+        return;
+    }
+
+    const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int n = 0; n < ntile; ++n) {
+        mbar_wait(&full[s], ph);
+        const TileMeta m = meta[s];
+        uint32_t bits = 0, quiet = 0;
+        if (m.nwin > 0) {
+            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) + tid * (kSeg / 8);
+            const int nvalid = m.nwin - tid * kWpt;
+            switch (m.e0 & 7) {                      // uniform over the CTA
+            case 0: shift_decode<kBf, kWpt, 0>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 1: shift_decode<kBf, kWpt, 1>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 2: shift_decode<kBf, kWpt, 2>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 3: shift_decode<kBf, kWpt, 3>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 4: shift_decode<kBf, kWpt, 4>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 5: shift_decode<kBf, kWpt, 5>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 6: shift_decode<kBf, kWpt, 6>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            default: shift_decode<kBf, kWpt, 7>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (m.nwin > 0) {
+            // kLanesPerWord threads hold the kWpt-bit pieces of one plane word
+            uint32_t bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
+            uint32_t qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
+#pragma unroll
+            for (int o = 1; o < kLanesPerWord; o <<= 1) {
+                bw |= __shfl_xor_sync(0xFFFFFFFFu, bw, o);
+                qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
+            }
+            const int word = (tid * kWpt) >> 5;
+            if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin) p.planes[m.word_base + word] = make_uint2(bw, qw);
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+    }
+}
+
 // ------------------------------------------------------------------------------ k_frame ----
 template <int kThreads, typename T>
 __device__ __forceinline__ T block_min(T v, T *scratch)
@@ -823,7 +957,7 @@ __device__ __forceinline__ uint32_t decode_byte(uint32_t v14, const uint8_t *lut
 }
 
 // kThreads x kWords plane words are searched per block step: <128,4> for ordinary captures,
-// <512,8> when a capture has more than 65536 windows (e.g. 64 KB payloads at 300 baud).
+// <512,8> when the captures average more than 65536 windows (e.g. 64 KB payloads at 300 baud).
 // idx_t = int unless a capture has 2^30 or more windows.
 template <int kThreads, int kWords, typename idx_t>
 __global__ void __launch_bounds__(kThreads) k_frame(const CapDesc *__restrict__ caps,
@@ -1042,6 +1176,7 @@ __global__ void __launch_bounds__(32) k_gate_multi(const int32_t *__restrict__ a
 struct Group {
     int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, stage_bytes = 0, stages = 0;
     int small_wpt = 0;            // > 0: k_demod_small<bf/8, small_wpt>
+    int shift_wpt = 0;            // > 0: k_demod_shift<bf, shift_wpt>
     size_t smem = 0;
     int grid = 0;
     std::vector<int32_t> caps, tile_first, tile_gpos;
@@ -1058,6 +1193,8 @@ struct Group {
 static cudaError_t demod_set_smem_attr()
 {
     cudaError_t e = cudaFuncSetAttribute(k_demod_small<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 #define X(NT, MG) \
@@ -1090,6 +1227,8 @@ struct AfskRxPlan {
     uint2 *d_planes = nullptr;
     int64_t plane_words = 0;
     int64_t max_windows = 0;
+    int64_t sum_windows = 0;      // over the captures decoded on the GPU
+    int64_t gpu_caps = 0;
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
@@ -1103,6 +1242,8 @@ constexpr size_t kDemodMaxStages = 3;
 
 static size_t demod_smem_bytes(const Group &g)
 {
+    if (g.shift_wpt)
+        return (size_t)g.stages * g.stage_bytes + kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t);
     if (g.small_wpt)
         return (size_t)g.stages * g.stage_bytes + (size_t)8 * (g.bf / 8 + 1) * 16 + kMaxStages * sizeof(TileMeta) +
                2 * kMaxStages * sizeof(uint64_t);
@@ -1130,6 +1271,18 @@ static bool configure_group(Group &g, int bf)
         g.nv = g.seg / 8 + 1;
         g.nt = g.nv; g.merge = 0;
         g.wt = kConsumerThreads * g.small_wpt;
+        g.stage_bytes = ((g.wt * bf * 2 + 16 + 256) + 127) & ~127;
+        g.stages = pick_stages(g.stage_bytes);
+        g.smem = demod_smem_bytes(g);
+        return true;
+    }
+    if (bf == 12 || bf == 20) {
+        // windows of 4 (mod 8) samples: k_demod_shift, 2 or 4 windows per thread
+        g.shift_wpt = bf == 12 ? 4 : 2;      // measured at 4000 baud: 4 windows per thread 6245 GB/s, 2 -> 5366
+        g.seg = bf * g.shift_wpt;
+        g.nv = g.seg / 8 + 1;
+        g.nt = g.nv; g.merge = 0;
+        g.wt = kConsumerThreads * g.shift_wpt;
         g.stage_bytes = ((g.wt * bf * 2 + 16 + 256) + 127) & ~127;
         g.stages = pick_stages(g.stage_bytes);
         g.smem = demod_smem_bytes(g);
@@ -1231,6 +1384,8 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
             const int64_t kmax = (d.n - bf + bf - 1) / bf;             // windows at clock 0
             const int64_t ntiles = (kmax + g.wt - 1) / g.wt;
             P->max_windows = std::max(P->max_windows, kmax);
+            P->sum_windows += kmax;
+            P->gpu_caps++;
             if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
             g.caps.push_back(c);
             g.tile_gpos.insert(g.tile_gpos.end(), (size_t)ntiles, (int32_t)g.caps.size() - 1);
@@ -1355,6 +1510,8 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         if (g.small_wpt == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.small_wpt == 4) k_demod_small<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.small_wpt == 2) k_demod_small<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);
         if (e0 && e1) {
             cudaEventRecord(e1, st);
@@ -1363,7 +1520,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     }
     if (P->max_windows >= ((int64_t)1 << 30))
         k_frame<512, 8, long long><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
-    else if (P->max_windows > 65536)
+    else if (P->sum_windows > 65536 * std::max<int64_t>(P->gpu_caps, 1))   // long captures on average
         k_frame<512, 8, int><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     else
         k_frame<128, 4, int><<<P->B, 128, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);

@@ -46,6 +46,19 @@ AMP_END = 14000
 #       {300,600,1200,2400,4000,6000} + 1 % each of 4800 / 9600 (exception parity), payloads
 #       log-uniform 16 B - 4 KB, per-capture thresholds / gains / training times
 WORKLOADS = {"c2": (1200, 1024, 4096), "c3": (6000, 1024, 16384), "c4": (300, 65536, 64), "c5": (0, 0, 12500)}
+
+
+def resolve_workload(name):
+    """c2..c5, or w<baud>: a tuning aid — 1 KB payloads at any decodable baud, about 2.4 G samples."""
+    if name in WORKLOADS:
+        return WORKLOADS[name]
+    if name.startswith("w") and name[1:].isdigit():
+        baud = int(name[1:])
+        per_capture = (baud // 4 * 2 + 4 + 14 * 1024) * (48000 // baud) + 4800
+        return (baud, 1024, max(64, int(2.4e9 // per_capture)))
+    raise SystemExit(f"unknown workload {name!r}")
+
+
 SIGMAS = np.array([0, 2000, 8000, 14000, 19000, 26000], dtype=np.float64)
 SIGMA_W = np.array([1, 2, 3, 2, 1, 1], dtype=np.float64) / 10.0
 WL = "c2"
@@ -54,7 +67,7 @@ WL = "c2"
 def set_workload(name, captures):
     global BAUD, PAYLOAD, WL
     WL = name
-    BAUD, PAYLOAD, default_b = WORKLOADS[name]
+    BAUD, PAYLOAD, default_b = resolve_workload(name)
     return captures if captures else default_b
 
 
@@ -239,7 +252,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--captures", type=int, default=0, help="captures per GPU (default: the workload's)")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", help="c2 (default, the line of record), c3, c4, c5 or w<baud>")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-captures", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")

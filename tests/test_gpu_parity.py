@@ -175,19 +175,29 @@ def test_random_sweep_vs_oracle(baud):
     s.close()
 
 
-def test_every_alignment_and_clock_offset():
+@pytest.mark.parametrize("baud", [1200, 300, 600, 2400, 4000, 6000, 3000, 2000, 800, 12000])
+def test_every_alignment_and_clock_offset(baud):
     """Capture start alignment (mod 8 samples) x clock offset (lead silence) — exercises every
-    (e0) weight table and the misaligned TMA copies."""
-    rng = np.random.default_rng(3)
-    fr = O.tx_frames(b"alignment!", 1200, 0.1)
+    (e0) weight table / unrolled alignment body of every demodulator variant (k_demod merge and
+    plain, k_demod_small, k_demod_shift) and the misaligned TMA copies.  Payloads are long enough
+    that a capture spans several tiles, the last one partial."""
+    rng = np.random.default_rng([3, baud])
+    fr = O.tx_frames(rng.integers(0, 256, 700 if baud >= 2000 else 40, dtype=np.uint8).tobytes(), baud, 0.1)
     caps = []
     for lead in range(0, 48):
         caps.append(_impair(fr, rng, lead=lead, sigma=3000))
         caps.append(np.zeros(int(rng.integers(1, 8)), np.int16))      # shifts the next capture's alignment
     samples, offsets = A.modem._concat(caps)
-    s = A.RxSession(offsets, 1200, 14000)
+    s = A.RxSession(offsets, baud, 14000)
     s.upload(samples); s.run()
-    _check_against_oracle(s.download(), caps, [1200] * len(caps), [14000] * len(caps))
+    _check_against_oracle(s.download(), caps, [baud] * len(caps), [14000] * len(caps))
+    # stage level: every decision / quiet flag of a few captures, not only the decoded span
+    for i in (0, 2, 14, 30):
+        o = O.rx_decode(caps[i], baud, 14000, want_bits=True)
+        if o["status"] == 0:
+            bits, _ = s.planes(i)
+            k0 = (o["train_end"] - o["clock"]) // (48000 // baud)
+            assert np.array_equal(bits[k0:k0 + o["nbits"]].astype(np.uint8), o["bits"]), (baud, i)
     s.close()
 
 
@@ -202,6 +212,11 @@ def test_threshold_edge_samples():
     for thr in (14000, 400, 0, 1, 70000, -5):
         b = A.Receiver(1200, 18000, thr).decode_batch(caps)
         _check_against_oracle(b, caps, [1200] * len(caps), [thr] * len(caps))
+    # the same sample soup through the other demodulator variants (ties between the mark and space
+    # correlations are common here: the floor-compare path)
+    for baud in (2400, 4000, 6000, 3000, 300, 800):
+        b = A.Receiver(baud, 18000, 400).decode_batch(caps)
+        _check_against_oracle(b, caps, [baud] * len(caps), [400] * len(caps))
 
 
 def test_empty_and_ragged_batches():

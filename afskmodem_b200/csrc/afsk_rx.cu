@@ -1288,6 +1288,10 @@ static bool configure_group(Group &g, int bf)
         g.smem = demod_smem_bytes(g);
         return true;
     }
+    // Segments of at most 48 samples per thread.  The thread stride in shared memory is 2 * seg bytes:
+    // 40 samples (80 B) is conflict-free for 128-bit loads and 48 is 2-way, both reach the HBM ceiling;
+    // 32 is 4-way (75-89 % of it: 1500 / 750 / 375 baud).  Measured and rejected: segments of 64
+    // samples in merge mode (8-way, 57 %) and two 32-sample windows per thread (k_demod_small<4,2>, 83 %).
     while ((bf >> g.tpw_log2) > 48 && g.tpw_log2 < 3) g.tpw_log2++;
     const int tpw = 1 << g.tpw_log2;
     g.seg = (bf + tpw - 1) / tpw;
@@ -1507,9 +1511,9 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        if (g.small_wpt == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt == 4) k_demod_small<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt == 2) k_demod_small<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        if (g.small_wpt && g.bf == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 16) k_demod_small<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 24) k_demod_small<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);

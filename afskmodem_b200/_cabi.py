@@ -133,10 +133,11 @@ class DeviceBuffer:
         p = C.c_void_p()
         check(lib().afsk_malloc(device, max(self.nbytes, 16), C.byref(p)))
         self.ptr = p.value
+        self._free, self._cptr = lib().afsk_free, p     # kept so that close() works during interpreter shutdown
 
     def close(self):
         if getattr(self, "ptr", None):
-            lib().afsk_free(self.device, C.c_void_p(self.ptr))
+            self._free(self.device, self._cptr)
             self.ptr = None
 
     __del__ = close
@@ -162,13 +163,14 @@ class PinnedArray:
         p = C.c_void_p()
         check(lib().afsk_host_alloc(max(n, 16), C.byref(p)))
         self._ptr = p.value
+        self._free, self._cptr = lib().afsk_host_free, p
         buf = (C.c_uint8 * max(n, 16)).from_address(self._ptr)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
 
     def close(self):
         if getattr(self, "_ptr", None):
             self.array = None
-            lib().afsk_host_free(C.c_void_p(self._ptr))
+            self._free(self._cptr)
             self._ptr = None
 
     __del__ = close

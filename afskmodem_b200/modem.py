@@ -191,6 +191,7 @@ class RxSession:
                                                      _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
                                                      C.byref(plan)))
         self.plan = plan
+        self._destroy = L.afsk_rx_plan_destroy               # kept for close() during interpreter shutdown
         po = C.POINTER(C.c_int64)()
         _cabi.check(L.afsk_rx_plan_out_offsets(plan, C.byref(po)))
         self.out_off = np.ctypeslib.as_array(po, shape=(self.B + 1,)).copy()
@@ -208,7 +209,7 @@ class RxSession:
 
     def close(self):
         if getattr(self, "plan", None):
-            _cabi.lib().afsk_rx_plan_destroy(self.plan)
+            self._destroy(self.plan)
             self.plan = None
         for b in ("d_out", "d_res", "d_samples"):
             buf = getattr(self, b, None)
@@ -634,6 +635,7 @@ class TxSession:
             raise NotImplementedError(L.afsk_last_error().decode())
         _cabi.check(rc)
         self.plan = plan
+        self._destroy = L.afsk_tx_plan_destroy
         po, pl = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
         _cabi.check(L.afsk_tx_plan_out_offsets(plan, C.byref(po), C.byref(pl)))
         self.out_off = np.ctypeslib.as_array(po, shape=(self.B + 1,)).copy()
@@ -643,7 +645,7 @@ class TxSession:
 
     def close(self):
         if getattr(self, "plan", None):
-            _cabi.lib().afsk_tx_plan_destroy(self.plan)
+            self._destroy(self.plan)
             self.plan = None
         for b in ("d_pay", "d_out"):
             buf = getattr(self, b, None)

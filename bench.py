@@ -62,6 +62,7 @@ def resolve_workload(name):
 SIGMAS = np.array([0, 2000, 8000, 14000, 19000, 26000], dtype=np.float64)
 SIGMA_W = np.array([1, 2, 3, 2, 1, 1], dtype=np.float64) / 10.0
 WL = "c2"
+TX_STATS = None
 
 
 def set_workload(name, captures):
@@ -160,9 +161,23 @@ def build_batch_on_gpu(B, rank, device):
     tx.upload()
     # synthesize straight into a torch-owned buffer (caller-owned device pointer through the C ABI)
     clean = torch.empty(int(tx.out_off[-1]) + 64, dtype=torch.int16, device=dev)
-    A._cabi.check(A._cabi.lib().afsk_tx_synth(tx.plan, ctypes.c_void_p(tx.d_pay.ptr), ctypes.c_void_p(clean.data_ptr()),
-                                              None))
+    synth = lambda: A._cabi.check(A._cabi.lib().afsk_tx_synth(tx.plan, ctypes.c_void_p(tx.d_pay.ptr),       # noqa: E731
+                                                              ctypes.c_void_p(clean.data_ptr()), None))
+    for _ in range(3):
+        synth()
     A._cabi.stream_sync(device)
+    # transmitter throughput on the same batch (rows a12-a14): k_synth writes 2 bytes per frame
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(5):
+        synth()
+    t1.record()
+    torch.cuda.synchronize(dev)
+    tx_ms = t0.elapsed_time(t1) / 5
+    frames = int(tx.out_len.astype(np.int64).sum())
+    global TX_STATS
+    TX_STATS = {"kernel": "k_synth", "frames": frames, "ms": tx_ms, "msamples_s": frames / tx_ms / 1e3,
+                "achieved_gbs_written": 2.0 * frames / tx_ms / 1e6, "launches": 5}
     lead, sigma, gain = spec["lead"], spec["sigma"], spec["gain"]
     clean_n = tx.out_len.astype(np.int64)
     lens = lead + clean_n
@@ -367,10 +382,21 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_ms = float(te.item()) / args.e2e_steps
         assert hb.total_payload_bytes() == decoded_bytes
+        # what the PCIe link alone allows: the same pinned buffer copied to the device, nothing else
+        # (outside the timed region; explains e2e, is not part of it)
+        sess_e = rx._cache[1]
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(2):
+            sess_e.d_samples.upload(pin.array[:total])
+        h1.record()
+        torch.cuda.synchronize(dev)
+        h2d_ms = h0.elapsed_time(h1) / 2
         e2e = {"value": all_samples / (e2e_ms / 1000) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": total * 2, "d2h_bytes_per_step": int(32 * B + hb.out_off[-1]),
                "api": "Receiver.decode_batch(pinned int16 samples, offsets, baud_rate=[...], amp_end_threshold=[...])",
-               "steps": args.e2e_steps}
+               "steps": args.e2e_steps, "h2d_only_ms": h2d_ms, "h2d_only_gbs": 2.0 * total / h2d_ms / 1e6,
+               "share_of_step_in_h2d": h2d_ms / e2e_ms}
         pin.close()
 
     if rank != 0:
@@ -390,12 +416,17 @@ def main():
     launches_per_decode = max(demod_launches, 1) / args.steps
     demod_avg_ms = demod_per_decode_ms / launches_per_decode
     achieved = 2.0 * total / (demod_per_decode_ms / 1000) / 1e9
-    traffic = None
+    traffic = read_ceiling = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("k_demod_c2_dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        # ncu dram bytes of the dominant launch, full-size default batch of that workload only
+        traffic = tj.get(f"k_demod_{WL}_dram_bytes_per_launch") if B == resolve_workload(WL)[2] else None
+        read_ceiling = tj.get("hbm_read_only_ceiling_gbs")
     roofline = {"kernel": "k_demod", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                # k_demod only reads; a read-only stream runs above the copy (read+write) peak on this part
+                "read_only_ceiling": read_ceiling, "frac_of_read_only_ceiling": achieved / read_ceiling if read_ceiling else None,
                 "algorithmic_bytes_per_launch": 2 * total / launches_per_decode, "avg_launch_ms": demod_avg_ms,
                 "launches_per_step": launches_per_decode,
                 "share_of_step": demod_per_decode_ms / (elapsed_ms / args.steps)}
@@ -429,7 +460,7 @@ def main():
                        "payloads_exact": exact, "captures_raising_like_reference": raising,
                        "parity_checked_vs_oracle": parity_checked},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * sess.launches,
-            "roofline": roofline, "cpu_baseline": cpu}
+            "roofline": roofline, "cpu_baseline": cpu, "tx": TX_STATS}
     print(json.dumps(line))
     sess.close()
     if world > 1:

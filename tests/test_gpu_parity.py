@@ -390,3 +390,26 @@ def test_abi_rejects_bad_arguments():
     rc = L.afsk_rx_decode(s.plan, C.c_void_p(d.ptr + 2), C.c_void_p(s.d_out.ptr), C.c_void_p(s.d_res.ptr), None)
     assert rc == _cabi.AFSK_E_ARG and b"aligned" in L.afsk_last_error()
     s.close(); d.close()
+
+
+def test_batch_cli_round_trip(tmp_path, capsys):
+    """tools/afsk_batch.py (batch counterpart of the reference's tx-demo-file.py / rx-demo-file.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("afsk_batch", os.path.join(os.path.dirname(__file__), "..", "tools", "afsk_batch.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    msgs = ["Hello World!", "Héellóo World!", "third"]
+    assert cli.main(["tx", "--out-dir", str(tmp_path), *msgs]) == 0
+    files = sorted(str(p) for p in tmp_path.glob("*.wav"))
+    assert len(files) == 3
+    # the files are what the reference's save() writes
+    for f, m in zip(files, msgs):
+        assert np.array_equal(A.modem.read_wav_frames(f), O.tx_frames(m.encode(), 1200, 0.5))
+    (tmp_path / "short.wav").write_bytes(open(files[0], "rb").read()[:44 + 2 * 1000])      # < 4096 frames
+    capsys.readouterr()
+    assert cli.main(["rx", "--stages", *files, str(tmp_path / "short.wav")]) == 0
+    out = capsys.readouterr().out.splitlines()
+    assert out[0].startswith(f"{files[0]}: Hello World!    [clock 0, training end 24160, 168 bits, 12 bytes]")
+    assert "Héellóo World!" in out[1] and "third" in out[2]
+    assert out[3].endswith("Could not decode.")
+    A.LOG_LEVEL = 5

@@ -63,6 +63,7 @@ SIGMAS = np.array([0, 2000, 8000, 14000, 19000, 26000], dtype=np.float64)
 SIGMA_W = np.array([1, 2, 3, 2, 1, 1], dtype=np.float64) / 10.0
 WL = "c2"
 TX_STATS = None
+E2E_FILES = {}
 
 
 def set_workload(name, captures):
@@ -272,6 +273,8 @@ def main():
     ap.add_argument("--cpu-captures", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the wav-file leg of the end-to-end measurement")
+    ap.add_argument("--file-captures", type=int, default=1024)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.captures = set_workload(args.workload, args.captures)
@@ -397,6 +400,36 @@ def main():
                "api": "Receiver.decode_batch(pinned int16 samples, offsets, baud_rate=[...], amp_end_threshold=[...])",
                "steps": args.e2e_steps, "h2d_only_ms": h2d_ms, "h2d_only_gbs": 2.0 * total / h2d_ms / 1e6,
                "share_of_step_in_h2d": h2d_ms / e2e_ms}
+        # ---- the same path from wav FILES (Receiver.load_batch: afsk_wav_load host threads -> pinned
+        #      buffer -> H2D spans overlapped -> decode -> Python objects), a bounded prefix of the batch
+        if rank == 0 and world == 1 and not args.no_files:
+            import shutil
+            import tempfile
+            nf = min(B, args.file_captures)
+            while nf > 1 and 2 * int(offsets[nf]) > 2_500_000_000:       # keep the temporary files under 2.5 GB
+                nf -= 1
+            root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+            tmpdir = tempfile.mkdtemp(prefix="afsk_bench_", dir=root)
+            try:
+                names = [os.path.join(tmpdir, f"cap{c:05d}.wav") for c in range(nf)]
+                A.modem.write_wav_batch(names, pin.array, offsets[:nf], np.diff(offsets[:nf + 1]))
+                rxf = A.Receiver(BAUD or 1200, 18000, AMP_END, device=local)
+                if WL != "c5":
+                    t0 = time.perf_counter()           # first call: plan, device and pinned allocations
+                    rxf.load_batch(names, string=False, errors="return", log=False)
+                    first_ms = (time.perf_counter() - t0) * 1e3
+                    dtf = 1e9
+                    for _ in range(3):
+                        t0 = time.perf_counter()
+                        got = rxf.load_batch(names, string=False, errors="return", log=False)
+                        dtf = min(dtf, time.perf_counter() - t0)
+                    assert [g if isinstance(g, bytes) else b"" for g in got] == [batch.payload(c) for c in range(nf)], "load_batch != decode"
+                    E2E_FILES.update({"value": float(offsets[nf]) / dtf / 1e6, "unit": "Msamples/s", "files": nf,
+                                      "ms": dtf * 1e3, "first_call_ms": first_ms, "file_bytes": int(2 * offsets[nf] + 44 * nf), "where": tmpdir.rsplit("/", 1)[0],
+                                      "api": "Receiver.load_batch(filenames, string=False)", "host_threads": os.cpu_count()})
+                rxf.close()
+            finally:
+                shutil.rmtree(tmpdir, ignore_errors=True)
         pin.close()
 
     if rank != 0:
@@ -460,7 +493,7 @@ def main():
                        "payloads_exact": exact, "captures_raising_like_reference": raising,
                        "parity_checked_vs_oracle": parity_checked},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * sess.launches,
-            "roofline": roofline, "cpu_baseline": cpu, "tx": TX_STATS}
+            "roofline": roofline, "cpu_baseline": cpu, "tx": TX_STATS, "e2e_files": E2E_FILES or None}
     print(json.dumps(line))
     sess.close()
     if world > 1:

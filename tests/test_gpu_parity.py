@@ -413,3 +413,88 @@ def test_batch_cli_round_trip(tmp_path, capsys):
     assert "Héellóo World!" in out[1] and "third" in out[2]
     assert out[3].endswith("Could not decode.")
     A.LOG_LEVEL = 5
+
+
+def test_host_buffer_entry_points_like_the_integration_stub():
+    """afsk_rx_decode_host / afsk_tx_synth_host / afsk_tx_num_samples / afsk_rx_out_capacity called with
+    plain ctypes arrays exactly as the stub in INTEGRATION.md does (no plan, no session)."""
+    import ctypes as C
+    L = _cabi.lib()
+    rng = np.random.default_rng(77)
+    # --- Transmitter.save stub: one payload per call
+    for baud, tt, msg in [(1200, 0.5, b"Hello World!"), (300, 0.1, b""), (6000, 0.5, bytes(range(256))), (4800, 0.5, b"uneven tones")]:
+        ts = int(baud * tt / 2)
+        pay = (C.c_uint8 * max(len(msg), 1)).from_buffer_copy(msg or b"\0")
+        n = L.afsk_tx_num_samples(baud, ts, len(msg), pay if baud == 4800 else None)
+        want = O.tx_frames(msg, baud, tt)
+        assert n == len(want), (baud, n, len(want))
+        out = np.zeros(n + 8, dtype=np.int16)
+        rc = L.afsk_tx_synth_host(0, pay, (C.c_int64 * 2)(0, len(msg)), 1, (C.c_int32 * 1)(baud), (C.c_int64 * 1)(ts),
+                                  out.ctypes.data_as(C.POINTER(C.c_int16)), (C.c_int64 * 2)(0, n + 8))
+        assert rc == 0, L.afsk_last_error()
+        assert np.array_equal(out[:n], want), baud
+    # --- Receiver.load stub: one capture per call, and a small batch whose first offset is not 0
+    caps = [_impair(O.tx_frames(b"Hello World!", 1200, 0.5), rng, lead=123, sigma=5000),
+            _impair(O.tx_frames(rng.integers(0, 256, 200, dtype=np.uint8).tobytes(), 1200, 0.1), rng, lead=7, sigma=9000),
+            np.zeros(100, np.int16), rng.integers(-32768, 32767, 9000).astype(np.int16)]
+    for x in caps:
+        cap = L.afsk_rx_out_capacity(len(x), 1200)
+        out = (C.c_uint8 * cap)()
+        res = _cabi.RxResult()
+        rc = L.afsk_rx_decode_host(0, x.ctypes.data_as(C.POINTER(C.c_int16)), (C.c_int64 * 2)(0, len(x)), 1,
+                                   (C.c_int32 * 1)(1200), (C.c_int32 * 1)(14000), out, (C.c_int64 * 2)(0, cap), C.byref(res))
+        assert rc == 0, L.afsk_last_error()
+        o = O.rx_decode(x, 1200, 14000)
+        assert (res.status, res.clock, res.train_end, res.nbits, res.nbytes) == (o["status"], o["clock"], o["train_end"], o["nbits"], o["nbytes"])
+        assert bytes(out[:res.nbytes]) == o["data"]
+    pad = 37                                         # captures start at sample 37 of the host buffer
+    samples = np.concatenate([np.zeros(pad, np.int16)] + caps)
+    off = np.cumsum([pad] + [len(c) for c in caps]).astype(np.int64)
+    B = len(caps)
+    caps_b = [int(L.afsk_rx_out_capacity(len(c), 1200)) for c in caps]
+    out_off = np.concatenate([[0], np.cumsum(caps_b)]).astype(np.int64)
+    out = np.zeros(int(out_off[-1]), np.uint8)
+    res = (_cabi.RxResult * B)()
+    rc = L.afsk_rx_decode_host(0, samples.ctypes.data_as(C.POINTER(C.c_int16)), off.ctypes.data_as(C.POINTER(C.c_int64)), B,
+                               (C.c_int32 * B)(*[1200] * B), (C.c_int32 * B)(*[14000] * B),
+                               out.ctypes.data_as(C.POINTER(C.c_uint8)), out_off.ctypes.data_as(C.POINTER(C.c_int64)), res)
+    assert rc == 0, L.afsk_last_error()
+    for i, x in enumerate(caps):
+        o = O.rx_decode(x, 1200, 14000)
+        assert (res[i].status, res[i].clock, res[i].nbits) == (o["status"], o["clock"], o["nbits"]), i
+        assert out[out_off[i]:out_off[i] + res[i].nbytes].tobytes() == o["data"], i
+
+
+def test_fuzz_arbitrary_signals_mixed_batch():
+    """Not modem signals at all: noise of several distributions, DC offsets, square waves at wrong rates,
+    sparse impulses, saturated runs — random lengths, every demodulator variant in ONE mixed batch.  The
+    reference decodes such input to *something* (or nothing); the GPU must agree bit for bit."""
+    rng = np.random.default_rng(2024)
+    bauds_pool = [300, 600, 1200, 2400, 4000, 6000, 3000, 2000, 1500, 800, 750, 480, 375, 12000]
+    caps, bauds, thrs = [], [], []
+    for k in range(140):
+        n = int(rng.choice([0, 1, 4095, 4096, 4097, int(rng.integers(4098, 40000))], p=[.02, .02, .03, .05, .05, .83]))
+        kind = k % 7
+        if kind == 0:
+            x = rng.integers(-32768, 32768, n)
+        elif kind == 1:
+            x = np.round(rng.normal(0, float(rng.choice([300, 520, 5000, 20000])), n))
+        elif kind == 2:
+            x = np.round(rng.normal(float(rng.choice([-20000, 600, 15000])), 3000, n))           # DC offset
+        elif kind == 3:
+            per = int(rng.integers(3, 90))
+            x = np.where((np.arange(n) // per) % 2 == 0, 30000, -30000) + rng.integers(-500, 500, n)   # wrong-rate square
+        elif kind == 4:
+            x = np.zeros(n); idx = rng.integers(0, max(n, 1), n // 50); x[idx] = rng.choice([-32768, 32767], len(idx))
+        elif kind == 5:
+            x = np.cumsum(rng.integers(-900, 901, n))                                               # random walk, clipped
+        else:
+            x = rng.choice(np.array([-32768, -513, -512, 0, 512, 513, 32767]), n)
+        caps.append(np.clip(x, -32768, 32767).astype(np.int16))
+        bauds.append(int(rng.choice(bauds_pool)))
+        thrs.append(int(rng.choice([14000, 8000, 300, 0, 30000])))
+    samples, offsets = A.modem._concat(caps)
+    s = A.RxSession(offsets, bauds, thrs)
+    s.upload(samples); s.run()
+    _check_against_oracle(s.download(), caps, bauds, thrs)
+    s.close()

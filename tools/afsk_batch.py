@@ -53,7 +53,7 @@ def main(argv=None) -> int:
                 line = "Could not decode."
             else:
                 line = repr(v) if args.bytes else v
-            if batch is not None and int(batch.status[i]) >= 0:
+            if batch is not None and int(batch.status[i]) >= 0 and int(batch.clock[i]) >= 0 and not isinstance(v, Exception):
                 line += (f"    [clock {int(batch.clock[i])}, training end {int(batch.train_end[i])}, "
                          f"{int(batch.nbits[i])} bits, {int(batch.nbytes[i])} bytes]")
             print(f"{f}: {line}")

@@ -498,3 +498,91 @@ def test_fuzz_arbitrary_signals_mixed_batch():
     s.upload(samples); s.run()
     _check_against_oracle(s.download(), caps, bauds, thrs)
     s.close()
+
+
+def _device_round_trip(payloads, baud, tt=0.5):
+    """encode on the GPU, decode the device-resident frames in place (ranges plan), return (RxBatch, TxSession)."""
+    ts = int(baud * tt / 2)
+    tx = A.TxSession(payloads, baud, ts)
+    tx.upload(); tx.run()
+    _cabi.stream_sync(0)
+    rx = A.RxSession(tx.out_off[:-1].copy(), baud, 14000, lengths=tx.out_len.astype(np.int64))
+    rx.bind(tx.d_out.ptr)
+    rx.run()
+    b = rx.download()
+    return b, tx, rx
+
+
+def test_config2_full_size_device_round_trip():
+    """BASELINE config #2 at FULL size — 4096 captures x 1 KB at 1200 baud (2.47 G samples, 4.9 GB) —
+    synthesized and decoded without leaving HBM: encode -> decode is the identity, every stage integer
+    is the one SURVEY §8 derives (clock 0, 604 training + terminator bits, 14336 coded bits)."""
+    rng = np.random.default_rng(22)
+    B = 4096
+    pls = [p.tobytes() for p in rng.integers(0, 256, size=(B, 1024), dtype=np.uint8)]
+    b, tx, rx = _device_round_trip(pls, 1200)
+    assert int(tx.out_len.sum()) == B * 602400
+    assert (b.status == 0).all() and (b.clock == 0).all() and (b.nbits == 14336).all() and (b.nbytes == 1024).all()
+    assert (b.train_end == 604 * 40).all()
+    assert b.payloads() == pls
+    rx.close(); tx.close()
+
+
+def test_config4_full_size_device_round_trip():
+    """BASELINE config #4 at full size: 64 captures x 64 KB at 300 baud (146.8 M samples each, 18.8 GB)."""
+    rng = np.random.default_rng(44)
+    B = 64
+    pls = [p.tobytes() for p in rng.integers(0, 256, size=(B, 65536), dtype=np.uint8)]
+    b, tx, rx = _device_round_trip(pls, 300)
+    assert (tx.out_len == 146830080).all()
+    assert (b.status == 0).all() and (b.clock == 0).all() and (b.nbits == 917504).all()
+    assert b.payloads() == pls
+    rx.close(); tx.close()
+
+
+@pytest.mark.parametrize("baud", [1200, 2400, 6000, 300])
+def test_hamming_corrects_one_flipped_bit_per_codeword(baud):
+    """encode -> corrupt -> decode: ONE coded bit of EVERY 7-bit codeword is replaced by the opposite tone
+    (a random position per codeword); ECC.decode (afskmodem.py:145-163) must return the payload unchanged.
+    With a second flip in some codewords the (mis)correction must equal the oracle's."""
+    import torch
+    rng = np.random.default_rng([7, baud])
+    B, P = 64, 256
+    bf = 48000 // baud
+    pls = [p.tobytes() for p in rng.integers(0, 256, size=(B, P), dtype=np.uint8)]
+    ts = int(baud * 0.5 / 2)
+    tx = A.TxSession(pls, baud, ts)
+    tx.upload(); tx.run(); _cabi.stream_sync(0)
+    host = tx.download().samples.copy()
+    x = torch.from_numpy(host).cuda()
+    ncw = 2 * P                                                       # codewords per capture
+    first = 2 * ts + 4                                                # first coded bit (training + terminator)
+    r = torch.from_numpy(rng.integers(0, 7, size=(B, ncw))).cuda()
+    starts = torch.from_numpy(tx.out_off[:-1].copy()).cuda()[:, None] + (first + 7 * torch.arange(ncw, device="cuda")[None, :] + r) * bf
+    idx = starts.reshape(-1, 1) + torch.arange(bf, device="cuda")[None, :]          # [B*ncw, bf]
+    q = bf // 4
+    pos = torch.arange(bf, device="cuda")
+    mark = torch.where((pos // q) % 2 == 0, 32767, -32768).to(torch.int16)             # afskmodem.py:80-85
+    space = torch.where(pos < bf // 2, 32767, -32768).to(torch.int16)                  # :68-77
+    is_mark = x[idx[:, q]] < 0                                                         # second quarter low <=> mark
+    x[idx] = torch.where(is_mark[:, None], space[None, :], mark[None, :])
+    flipped = x.cpu().numpy()
+    rx = A.RxSession(tx.out_off[:-1].copy(), baud, 14000, lengths=tx.out_len.astype(np.int64))
+    rx.upload(flipped); rx.run()
+    b = rx.download()
+    assert (b.nbits == 14 * P).all()
+    assert b.payloads() == pls, "single-bit errors must be corrected"
+    # a second flip in the first 40 codewords of every capture: miscorrection, identical to the oracle's
+    r2 = (r[:, :40] + 1 + torch.from_numpy(rng.integers(0, 6, size=(B, 40))).cuda()) % 7
+    starts2 = torch.from_numpy(tx.out_off[:-1].copy()).cuda()[:, None] + (first + 7 * torch.arange(40, device="cuda")[None, :] + r2) * bf
+    idx2 = starts2.reshape(-1, 1) + torch.arange(bf, device="cuda")[None, :]
+    is_mark2 = x[idx2[:, q]] < 0
+    x[idx2] = torch.where(is_mark2[:, None], space[None, :], mark[None, :])
+    twice = x.cpu().numpy()
+    rx.upload(twice); rx.run()
+    b2 = rx.download()
+    assert b2.payloads() != pls
+    for i in (0, B // 2, B - 1):
+        o = O.rx_decode(twice[int(tx.out_off[i]):int(tx.out_off[i]) + int(tx.out_len[i])], baud, 14000)
+        assert (int(b2.nbits[i]), b2.payload(i)) == (o["nbits"], o["data"])
+    rx.close(); tx.close()

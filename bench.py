@@ -270,7 +270,7 @@ def main():
     ap.add_argument("--captures", type=int, default=0, help="captures per GPU (default: the workload's)")
     ap.add_argument("--workload", default="c2", help="c2 (default, the line of record), c3, c4, c5 or w<baud>")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-captures", type=int, default=2048)
+    ap.add_argument("--cpu-captures", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the wav-file leg of the end-to-end measurement")
@@ -290,6 +290,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Topology-aware placement: with fewer ranks than visible GPUs, spread the ranks over the box
+    # (rank r -> GPU r * ndev / world).  Measured on the 8-GPU box (tools/scratch/h2d_scaling.py): four
+    # ranks on GPUs 0-3 copy from pinned host memory at 28.7 GB/s each (one half of the host's PCIe
+    # fabric carries ~115 GB/s), on GPUs 0,2,4,6 at 53.1 GB/s each.  Device-resident numbers do not care.
+    ndev = torch.cuda.device_count()
+    if world > 1 and ndev >= 2 * world and os.environ.get("AFSK_BENCH_SPREAD", "1") != "0":
+        local *= ndev // world
     A.LOG_LEVEL = 5
     _cabi.require_device(local)              # no CPU fallback
     torch.cuda.set_device(local)
@@ -490,6 +497,7 @@ def main():
             "config": {"workload": workload_name(B), "captures_per_gpu": B, "samples_per_gpu": total,
                        "baud": BAUD or "mixed", "payload_bytes": PAYLOAD or "16-4096",
                        "l2_policy": f"inputs ({2 * total / 1e9:.1f} GB/GPU) larger than L2; no flush",
+                       "gpu_of_rank0": local, "gpus_visible": ndev, "rank_to_gpu_stride": (ndev // world if (world > 1 and ndev >= 2 * world and os.environ.get("AFSK_BENCH_SPREAD", "1") != "0") else 1),
                        "payloads_exact": exact, "captures_raising_like_reference": raising,
                        "parity_checked_vs_oracle": parity_checked},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * sess.launches,

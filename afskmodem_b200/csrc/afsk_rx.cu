@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
                 uint32_t qw = __ballot_sync(0xFFFFFFFFu, quiet);
                 const int per_warp = 32 >> p.tpw_log2;
                 const int w0 = warp * per_warp;
-                if (lane == 0 && w0 < m.nwin) {
+                if (lane == 0 && (w0 & ~31) < m.nwin) {          // every piece of a word that holds a valid window
                     uint8_t *dst = reinterpret_cast<uint8_t *>(p.planes + m.word_base + (w0 >> 5)) + ((w0 & 31) >> 3);
                     if (p.tpw_log2 == 1) {
                         bw = squeeze2(bw); qw = squeeze2(qw);
@@ -1413,6 +1413,8 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     up((void **)&P->d_caps, P->caps.data(), sizeof(CapDesc) * B);
     if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_clock, sizeof(int32_t) * (B ? B : 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_planes, sizeof(uint2) * P->plane_words);
+    // k_frame may load (and mask / shift out) plane words past a capture's last window: keep them defined
+    if (e == cudaSuccess) e = cudaMemset(P->d_planes, 0, sizeof(uint2) * P->plane_words);
     for (Group &g : P->groups) {
         up((void **)&g.d_caps, g.caps.data(), sizeof(int32_t) * g.caps.size());
         up((void **)&g.d_tile_first, g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());

@@ -204,6 +204,8 @@ class RxSession:
             self.total_samples = int((self.offsets + self.lengths).max()) if self.B else 0
         self.d_out = DeviceBuffer(device, int(self.out_off[-1]))
         self.d_res = DeviceBuffer(device, 32 * max(self.B, 1))
+        # payloads are written at capacity offsets: keep the gaps between them defined (zero)
+        _cabi.check(L.afsk_memset(device, C.c_void_p(self.d_out.ptr), 0, max(int(self.out_off[-1]), 16), None))
         self.d_samples = None
         self._ext_ptr = None
 

@@ -55,6 +55,23 @@ __device__ __forceinline__ uint32_t afsk_smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));   // volatile: stays behind the barrier
+    return v;
+}
+// predicated shared-memory load: the result is undefined (and the address not touched) when !pred
+__device__ __forceinline__ uint32_t lds_u32_if(uint32_t addr, bool pred)
+{
+    uint32_t v;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p ld.shared.u32 %0, [%1];\n\t}"
+        : "=r"(v)
+        : "r"(addr), "r"((uint32_t)pred));
+    return v;
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(afsk_smem_u32(bar)), "r"(count));

@@ -33,6 +33,7 @@ constexpr int kConsumerThreads = 256;
 constexpr int kDemodThreads = kConsumerThreads + 32;   // + one producer warp
 constexpr int kMaxStages = 8;
 constexpr int kClockThreads = 128;
+constexpr int kClockChain = 35;     // candidates per chain in k_clock
 constexpr int kFrameThreads = 128;    // k_gate_scan block; k_frame is templated on its own block size
 
 struct __align__(16) CapDesc {
@@ -85,6 +86,7 @@ __device__ __forceinline__ long long num_windows(long long n, int bf, int clk)
 }
 
 // ------------------------------------------------------------------------------ k_clock ----
+template <bool kV1>
 __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restrict__ x,
                                                          const CapDesc *__restrict__ caps,
                                                          int32_t *__restrict__ clock,
@@ -161,32 +163,105 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     }
     __syncthreads();
 
-    const int bf = d.bf, q = bf >> 2, h = bf >> 1;
+    if constexpr (kV1) {   // previous candidate loop (seven taps per candidate), kept for the same-box A/B
+        const int bf = d.bf, q = bf >> 2, h = bf >> 1;
+        const int span = AFSK_SYNC_FRAMES - 2 * bf;                 // :327
+        const uint32_t c0 = 65535u * (uint32_t)bf;
+        const uint32_t div = 2u * (uint32_t)bf;
+        // getDiff(i) = floor(D_i / 2bf) is monotone in D_i, so the first strict minimum (:332-337) is the
+        // first i with D_i <= T where T = (floor(min D / 2bf) + 1) * 2bf - 1: one division per capture.
+        constexpr int kPerThread = AFSK_SYNC_FRAMES / kClockThreads;   // 32 candidates per thread at most
+        uint32_t Dv[kPerThread];
+        uint32_t best = 0xFFFFFFFFu;
+        // seven prefix taps per candidate, candidate i = tid + 128 k (conflict-free: consecutive lanes,
+        // consecutive words); the last partial round reads up to 127 words past the scanned range
+        // (inside Qs, values unused)
+        const uint32_t *p0 = P + tid + e, *p1 = p0 + q, *p2 = p0 + 2 * q, *p3 = p0 + 3 * q, *p4 = p0 + bf,
+                       *p5 = p0 + bf + h, *p6 = p0 + 2 * bf;
+        const int kmax = (span + kClockThreads - 1) / kClockThreads;
+    #pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            uint32_t D = 0xFFFFFFFFu;
+            if (k < kmax) {
+                const int o = k * kClockThreads;
+                // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO)
+                D = c0 + p0[o] + p6[o] - 2u * (p1[o] - p2[o] + p3[o] - p4[o] + p5[o]);
+                D = (tid + o < span) ? D : 0xFFFFFFFFu;
+            }
+            Dv[k] = D;
+            best = min(best, D);
+        }
+    #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+        if (lane == 0) warp_min[warp] = best;
+        __syncthreads();
+        best = warp_min[0];
+    #pragma unroll
+        for (int w = 1; w < kClockThreads / 32; w++) best = min(best, warp_min[w]);
+        const uint32_t T = (best / div + 1u) * div - 1u;            // getDiff :107
+        uint32_t first = 0xFFFFFFFFu;
+    #pragma unroll
+        for (int k = kPerThread - 1; k >= 0; k--)
+            if (Dv[k] <= T) first = (uint32_t)(tid + k * kClockThreads);
+    #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+        __syncthreads();
+        if (lane == 0) warp_min[warp] = first;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kClockThreads / 32; w++) first = min(first, warp_min[w]);
+            clock[c] = (int32_t)first;
+        }
+        return;
+    } else {
+    const int bf = d.bf, q = bf >> 2;
     const int span = AFSK_SYNC_FRAMES - 2 * bf;                 // :327
     const uint32_t c0 = 65535u * (uint32_t)bf;
     const uint32_t div = 2u * (uint32_t)bf;
     // getDiff(i) = floor(D_i / 2bf) is monotone in D_i, so the first strict minimum (:332-337) is the
     // first i with D_i <= T where T = (floor(min D / 2bf) + 1) * 2bf - 1: one division per capture.
-    constexpr int kPerThread = AFSK_SYNC_FRAMES / kClockThreads;   // 32 candidates per thread at most
-    uint32_t Dv[kPerThread];
+    //
+    // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO) is
+    //     D_i = c0 + t0 + t8 - 2 (t1 - t2 + t3 - t4 + t6),   t_m = P[i + m q]
+    // and candidate i + q uses t1..t9: a thread walks a CHAIN i, i + q, i + 2q, ... with the nine taps in
+    // registers and ONE new shared-memory word per candidate (instead of seven).  The candidates are
+    // tiled in blocks of q * kClockChain; item (block b, residue a) is the chain starting at a + q * kClockChain * b,
+    // so consecutive threads read consecutive words.  Every decodable baud from 300 up gives at most 128
+    // items (one per thread); rarer geometries take further items through the direct seven-tap form.
+    const uint32_t *Pe = P + e;
+    const int qL = q * kClockChain;
+    const int nitems = ((span + qL - 1) / qL) * q;
+    constexpr int kPmax = AFSK_SYNC_FRAMES + 7;                // last prefix entry a valid candidate can touch
+    auto D_at = [&](int i) -> uint32_t {
+        return c0 + Pe[i] + Pe[i + 8 * q] - 2u * (Pe[i + q] - Pe[i + 2 * q] + Pe[i + 3 * q] - Pe[i + 4 * q] + Pe[i + 6 * q]);
+    };
+    uint32_t Dv[kClockChain];
     uint32_t best = 0xFFFFFFFFu;
-    // seven prefix taps per candidate, candidate i = tid + 128 k (conflict-free: consecutive lanes,
-    // consecutive words); the last partial round reads up to 127 words past the scanned range
-    // (inside Qs, values unused)
-    const uint32_t *p0 = P + tid + e, *p1 = p0 + q, *p2 = p0 + 2 * q, *p3 = p0 + 3 * q, *p4 = p0 + bf,
-                   *p5 = p0 + bf + h, *p6 = p0 + 2 * bf;
-    const int kmax = (span + kClockThreads - 1) / kClockThreads;
+    const int s0 = (tid % q) + qL * (tid / q);                  // first candidate of this thread's chain
+    // kv valid candidates in the chain (a suffix may lie beyond the span, or the whole item may not exist);
+    // a valid candidate reads P[.. 4103] at most, so loads guarded by k < kv stay inside Qs
+    int kv = tid < nitems ? (span - s0 + q - 1) / q : 0;
+    kv = kv < 0 ? 0 : (kv > kClockChain ? kClockChain : kv);
+    {
+        uint32_t t[9];
+        uint32_t ta = afsk_smem_u32(P + (kv > 0 ? s0 + e : 0));
+        const uint32_t tstep = 4u * (uint32_t)q;
 #pragma unroll
-    for (int k = 0; k < kPerThread; k++) {
-        uint32_t D = 0xFFFFFFFFu;
-        if (k < kmax) {
-            const int o = k * kClockThreads;
-            // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO)
-            D = c0 + p0[o] + p6[o] - 2u * (p1[o] - p2[o] + p3[o] - p4[o] + p5[o]);
-            D = (tid + o < span) ? D : 0xFFFFFFFFu;
+        for (int m = 0; m < 8; m++) { t[m] = lds_u32(ta); ta += tstep; }
+#pragma unroll
+        for (int k = 0; k < kClockChain; k++) {
+            t[8] = lds_u32_if(ta, k < kv);                      // undefined for k >= kv (never used)
+            ta += tstep;
+            const uint32_t D = c0 + t[0] + t[8] - 2u * (t[1] - t[2] + t[3] - t[4] + t[6]);
+            Dv[k] = D;                                          // garbage for k >= kv: masked below
+            if (k < kv) best = min(best, D);
+#pragma unroll
+            for (int m = 0; m < 8; m++) t[m] = t[m + 1];
         }
-        Dv[k] = D;
-        best = min(best, D);
+    }
+    for (int it = tid + kClockThreads; it < nitems; it += kClockThreads) {
+        const int s1 = (it % q) + qL * (it / q);
+        for (int k = 0, i = s1; k < kClockChain && i < span; k++, i += q) best = min(best, D_at(i));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
@@ -197,9 +272,19 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     for (int w = 1; w < kClockThreads / 32; w++) best = min(best, warp_min[w]);
     const uint32_t T = (best / div + 1u) * div - 1u;            // getDiff :107
     uint32_t first = 0xFFFFFFFFu;
+    {
+        // smallest k with Dv[k] <= T; if that k is not a valid candidate, no valid one qualifies
+        int kf = kClockChain;
 #pragma unroll
-    for (int k = kPerThread - 1; k >= 0; k--)
-        if (Dv[k] <= T) first = (uint32_t)(tid + k * kClockThreads);
+        for (int k = kClockChain - 1; k >= 0; k--)
+            if (Dv[k] <= T) kf = k;
+        if (kf < kv) first = (uint32_t)(s0 + kf * q);
+    }
+    for (int it = tid + kClockThreads; it < nitems; it += kClockThreads) {
+        const int s1 = (it % q) + qL * (it / q);
+        for (int k = 0, i = s1; k < kClockChain && i < span; k++, i += q)
+            if (D_at(i) <= T) { first = min(first, (uint32_t)i); break; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
     __syncthreads();
@@ -208,6 +293,7 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     if (tid == 0) {
         for (int w = 1; w < kClockThreads / 32; w++) first = min(first, warp_min[w]);
         clock[c] = (int32_t)first;
+    }
     }
 }
 
@@ -675,11 +761,189 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
 // Short windows (bf = 8, 16, 24: 6000 / 3000 / 2000 baud): one thread decodes kWpt consecutive
 // windows of kM vectors each, so the per-tile bookkeeping is paid once per 48-64 samples instead of
 // once per 8-24.  Every vector is re-aligned to the window grid with 4 PRMTs (slots >= e from
+// vector i, slots < e from vector i+1); the weights are uniform over the tile (alignment e is per
+// tile) and live in registers; threads visit their windows in a lane-rotated order so that the
+// 128-bit shared-memory loads of a warp fall in different banks.  The window body is branch-free
+// and carries ONE packed accumulator, D = (mark - space) / 2 as in k_demod's merge mode: the byte
+// offsets and plane-bit masks of a thread's windows are per-thread constants, windows whose
+// correlations tie (noise only) are collected in a mask and re-decided from the full sums after the
+// loop, and windows past the end of the capture are masked once per tile.
+template <int kM>
+__device__ __forceinline__ bool small_tie_decide(const uint4 *dp, const uint4 *wt, uint32_t k512)
+{
+    // full mark / space sums of one window (the decision of k_demod's plain mode)
+    constexpr int kBf = 8 * kM;
+    const uint4 sel = wt[kM];
+    int accM = 0, accS = 0, accA = 0;
+    uint4 cur = dp[0];
+#pragma unroll
+    for (int i = 0; i < kM; i++) {
+        const uint4 nxt = dp[i + 1];
+        const uint4 W = wt[i];
+        const uint32_t x0 = prmt(cur.x, nxt.x, sel.x), x1 = prmt(cur.y, nxt.y, sel.y);
+        const uint32_t x2 = prmt(cur.z, nxt.z, sel.z), x3 = prmt(cur.w, nxt.w, sel.w);
+        accum4_full(x0, x1, W.x, W.z, k512, accM, accS, accA);
+        accum4_full(x2, x3, W.y, W.w, k512, accM, accS, accA);
+        cur = nxt;
+    }
+    // acc = 256 * T.n + T.c with |T.c| <= 24
+    const int Um = (int)((unsigned)accM << 24) >> 24, Us = (int)((unsigned)accS << 24) >> 24;
+    const int du = Um - Us;
+    bool b1 = du > 0;
+    if (du == 0) {
+        const int Nm = (accM - Um) >> 8, Ns = (accS - Us) >> 8;
+        if (Ns > Nm) {
+            const int M2 = 65535 * kBf - 65534 * Um + 2 * Nm;
+            const int S2 = M2 + 2 * (Ns - Nm);
+            b1 = (S2 - M2 >= 2 * kBf) || (M2 < (S2 / (2 * kBf)) * (2 * kBf));   // floor(M/bf) < floor(S/bf)
+        }
+    }
+    return b1;
+}
+
+template <int kM, int kWpt>
+__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.stages;
+    uint8_t *stage_base = smem;
+    // per alignment e: [0, kM) mark / space weights, [kM] PRMT selectors, [kM + 1, 2 kM + 1) D weights
+    constexpr int kEnt = 2 * kM + 1;
+    uint4 *wtab = reinterpret_cast<uint4 *>(smem + (size_t)S * p.stage_bytes);     // [8 alignments][kEnt]
+    TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + 8 * kEnt);
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
+    uint64_t *empty = full + kMaxStages;
+    constexpr int kBf = 8 * kM, kSeg = kBf * kWpt, kLanesPerWord = 32 / kWpt;
+
+    // weights of re-aligned vector i at alignment e: slot s holds window sample 8i + ((s - e) mod 8)
+    if (tid < 8 * kEnt) {
+        const int e = tid / kEnt, i = tid % kEnt;
+        if (i == kM) {
+            uint32_t sel[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) sel[j] = (2 * j >= e) ? 0x3210u : ((2 * j + 1 < e) ? 0x7654u : 0x3254u);
+            wtab[tid] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
+        } else {
+            const int iv = i < kM ? i : i - kM - 1;
+            const int q = kBf >> 2;
+            uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u};
+#pragma unroll
+            for (int sl = 0; sl < 8; sl++) {
+                const int r = 8 * iv + ((sl - e + 8) & 7), qd = r / q, sh = 8 * (sl & 3);
+                mk[sl >> 2] |= ((qd & 1) ? 0xFFu : 0x01u) << sh;
+                sp[sl >> 2] |= ((qd & 2) ? 0xFFu : 0x01u) << sh;
+            }
+            if (i < kM) {
+                wtab[tid] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
+            } else {
+                // D = (mark - space) / 2: the mark weight where the two differ (0x01 ^ 0xFF = 0xFE), else 0
+                const uint32_t x0 = mk[0] ^ sp[0], x1 = mk[1] ^ sp[1];
+                wtab[tid] = make_uint4(mk[0] & prmt(x0, x0, 0xBA98u), mk[1] & prmt(x1, x1, 0xBA98u), 0u, 0u);
+            }
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
+    if (ntile <= 0) return;
+    if (warp == kConsumerThreads / 32) {
+        demod_produce(p, ntile, stage_base, meta, full, empty);
+        return;
+    }
+
+    const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
+    // the thread's j-th visit is to its window (j + tid) mod kWpt: byte offset in the tile and plane bit
+    uint32_t woff[kWpt], wbit[kWpt];
+#pragma unroll
+    for (int j = 0; j < kWpt; j++) {
+        const int jj = (j + tid) & (kWpt - 1);
+        woff[j] = (uint32_t)(tid * kSeg + jj * kBf) * 2u;
+        wbit[j] = 1u << jj;
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int n = 0; n < ntile; ++n) {
+        mbar_wait(&full[s], ph);
+        const TileMeta m = meta[s];
+        uint32_t bits = 0, quiet = 0;
+        if (m.nwin > 0) {
+            const uint4 *wt = wtab + (m.e0 & 7) * kEnt;
+            uint2 Dw[kM];
+#pragma unroll
+            for (int i = 0; i < kM; i++) Dw[i] = *reinterpret_cast<const uint2 *>(wt + kM + 1 + i);
+            const uint4 sel = wt[kM];
+            // kSeg % 8 == 0: the thread's first vector is e0 / 8 + tid * kSeg / 8
+            const uint8_t *tb = stage_base + (size_t)s * p.stage_bytes + (m.e0 >> 3) * 16;
+            uint32_t ties = 0;
+#pragma unroll
+            for (int j = 0; j < kWpt; j++) {
+                const uint4 *dp = reinterpret_cast<const uint4 *>(tb + woff[j]);
+                int accD = 0, accA = 0;
+                uint4 cur = dp[0];
+#pragma unroll
+                for (int i = 0; i < kM; i++) {
+                    const uint4 nxt = dp[i + 1];
+                    const uint32_t x0 = prmt(cur.x, nxt.x, sel.x), x1 = prmt(cur.y, nxt.y, sel.y);
+                    const uint32_t x2 = prmt(cur.z, nxt.z, sel.z), x3 = prmt(cur.w, nxt.w, sel.w);
+                    accum4_d(x0, x1, Dw[i].x, k512, accD, accA);
+                    accum4_d(x2, x3, Dw[i].y, k512, accD, accA);
+                    cur = nxt;
+                }
+                // accD = 256 * D.n + D.c with |D.c| <= 12: D.c = (Um - Us) / 2 decides; when it is zero the
+                // window is a 0 unless Ns > Nm (D.n < 0), and only then are the two floors compared
+                const int dl = (int)((unsigned)accD << 24);
+                if (dl > 0) bits |= wbit[j];
+                if (dl == 0 && accD < 0) ties |= wbit[j];
+                if (accA < m.thr_bf) quiet |= wbit[j];
+            }
+            if (ties) {
+                for (int jj = 0; jj < kWpt; jj++)
+                    if ((ties >> jj) & 1u) {
+                        const uint4 *dp = reinterpret_cast<const uint4 *>(tb + (uint32_t)(tid * kSeg + jj * kBf) * 2u);
+                        if (small_tie_decide<kM>(dp, wt, k512)) bits |= 1u << jj;
+                    }
+            }
+            // windows past the capture's last one
+            const int nvalid = m.nwin - tid * kWpt;
+            const uint32_t vm = nvalid >= kWpt ? 0xFFFFFFFFu : (nvalid <= 0 ? 0u : (1u << nvalid) - 1u);
+            bits &= vm;
+            quiet &= vm;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (m.nwin > 0) {
+            // kLanesPerWord threads hold the kWpt-bit pieces of one plane word
+            uint32_t bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
+            uint32_t qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
+#pragma unroll
+            for (int o = 1; o < kLanesPerWord; o <<= 1) {
+                bw |= __shfl_xor_sync(0xFFFFFFFFu, bw, o);
+                qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
+            }
+            const int word = (tid * kWpt) >> 5;
+            if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin) p.planes[m.word_base + word] = make_uint2(bw, qw);
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+    }
+}
+
+// ---- k_demod_small_v1: previous version, kept for the same-box A/B (AFSK_SMALL_V1=1) ----
+// Short windows (bf = 8, 16, 24: 6000 / 3000 / 2000 baud): one thread decodes kWpt consecutive
+// windows of kM vectors each, so the per-tile bookkeeping is paid once per 48-64 samples instead of
+// once per 8-24.  Every vector is re-aligned to the window grid with 4 PRMTs (slots >= e from
 // vector i, slots < e from vector i+1), the +/-1 weights are uniform over the tile (alignment e is
 // per tile) and live in registers, and threads visit their windows in a lane-rotated order so that
 // the 128-bit shared-memory loads of a warp fall in different banks.
 template <int kM, int kWpt>
-__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodParams p)
+__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small_v1(const DemodParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1059,6 +1323,111 @@ __global__ void __launch_bounds__(kThreads) k_frame(const CapDesc *__restrict__ 
     }
 }
 
+// One WARP per capture (four captures per CTA) for batches of ordinary captures: the two find-first
+// searches reduce with one REDUX per step instead of a CTA-wide barrier pair, no shared scratch, and
+// four times as many captures are in flight per SM.  Same arithmetic as k_frame above; used when no
+// capture of the batch has more than kFrameWarpMaxWindows windows.
+constexpr int kFrameWarpCaps = 4;                      // warps (captures) per CTA
+constexpr int64_t kFrameWarpMaxWindows = 262144;       // 8192 plane words: 64 search steps of one warp
+
+__global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDesc *__restrict__ caps,
+                                                                    const int32_t *__restrict__ clock,
+                                                                    const uint2 *__restrict__ planes,
+                                                                    uint8_t *__restrict__ out,
+                                                                    AfskRxResult *__restrict__ res, int B)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ uint8_t lut[128];
+    static_assert(32 * kFrameWarpCaps == 128, "one LUT entry per thread");
+    lut[tid] = (uint8_t)hamming74_nibble((uint32_t)tid);
+    __syncthreads();
+    const int c = blockIdx.x * kFrameWarpCaps + (tid >> 5);
+    if (c >= B) return;
+    const CapDesc d = caps[c];
+    if (d.status0 != 0) return;
+    const int clk = clock[c];
+    const int K = (int)num_windows(d.n, d.bf, clk);
+    const int nwords = (K + 31) >> 5;
+    const uint2 *PL = planes + d.plane_base;
+    constexpr unsigned NONE = 0x7FFFFFFFu;
+    constexpr int kWords = 4;                           // plane words per lane per step
+
+    // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
+    unsigned kterm = NONE;
+    for (int base = 0; base < nwords; base += 32 * kWords) {
+        unsigned cand = NONE;
+#pragma unroll
+        for (int r = kWords - 1; r >= 0; r--) {
+            const int j = base + lane + 32 * r;
+            if (j < nwords) {
+                const uint32_t cur = PL[j].x, prev = j ? PL[j - 1].x : 0u;
+                // bit t of M: b[k-3] & ~b[k-2] & ~b[k-1] & ~b[k] for k = 32j + t
+                uint32_t M = __funnelshift_l(prev, cur, 3) & ~__funnelshift_l(prev, cur, 2) &
+                             ~__funnelshift_l(prev, cur, 1) & ~cur;
+                const int rem = K - 32 * j;
+                if (rem < 32) M &= (1u << rem) - 1u;
+                if (M) cand = (unsigned)(32 * j + (__ffs(M) - 1));
+            }
+        }
+        kterm = __reduce_min_sync(0xFFFFFFFFu, cand);
+        if (kterm != NONE) break;
+    }
+    const int k0 = (kterm == NONE) ? K : (int)kterm + 1;
+    // phase 2 (:372-378): first quiet window at or after k0
+    unsigned kq = NONE;
+    for (int base = k0 >> 5; base < nwords; base += 32 * kWords) {
+        unsigned cand = NONE;
+#pragma unroll
+        for (int r = kWords - 1; r >= 0; r--) {
+            const int j = base + lane + 32 * r;
+            if (j < nwords) {
+                uint32_t M = PL[j].y;
+                if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
+                const int rem = K - 32 * j;
+                if (rem < 32) M &= (1u << rem) - 1u;
+                if (M) cand = (unsigned)(32 * j + (__ffs(M) - 1));
+            }
+        }
+        kq = __reduce_min_sync(0xFFFFFFFFu, cand);
+        if (kq != NONE) break;
+    }
+    const int k1 = (kq == NONE) ? K : (int)kq;
+    const int nbits = k1 - k0;
+    const int nbytes = (nbits / 7) / 2;              // ECC.decode :156, __bitsToBytes :396
+    uint8_t *o = out + d.out_off;                    // 16-byte aligned
+    // four bytes (56 coded bits) per lane step: three plane words, one 32-bit store
+    const int nquad = nbytes >> 2;
+    for (int i = lane; i < nquad; i += 32) {
+        const int pos = k0 + 56 * i;
+        const int wi = pos >> 5;
+        const uint32_t sh = (uint32_t)(pos & 31);
+        const uint32_t w0 = PL[wi].x, w1 = PL[wi + 1].x, w2 = PL[wi + 2].x;
+        uint32_t word = 0;
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++) {
+            const uint32_t sft = sh + 14u * jb;                 // 0 .. 73
+            const uint32_t a = sft < 32 ? w0 : (sft < 64 ? w1 : w2);
+            const uint32_t bb = sft < 32 ? w1 : (sft < 64 ? w2 : 0u);
+            word |= decode_byte(__funnelshift_r(a, bb, sft & 31u) & 0x3FFFu, lut) << (8 * jb);
+        }
+        reinterpret_cast<uint32_t *>(o)[i] = word;
+    }
+    for (int i = 4 * nquad + lane; i < nbytes; i += 32) {
+        const int pos = k0 + 14 * i;
+        const uint32_t lo = PL[pos >> 5].x, hi = PL[(pos >> 5) + 1].x;
+        o[i] = (uint8_t)decode_byte(__funnelshift_r(lo, hi, (uint32_t)(pos & 31)) & 0x3FFFu, lut);
+    }
+    if (lane == 0) {
+        AfskRxResult r;
+        r.status = nbits > 0 ? AFSK_ST_OK : AFSK_ST_NO_DATA;
+        r.clock = clk;
+        r.train_end = (long long)clk + (long long)k0 * d.bf;   // "Training sequence terminated on frame" :368
+        r.nbits = nbits;
+        r.nbytes = nbits > 0 ? nbytes : 0;
+        res[c] = r;
+    }
+}
+
 // ------------------------------------------------------------------------------- k_gate ----
 // Receiver.__listen (:299-319) arithmetic: per-2048-frame chunk amplitude, then open/close search.
 __global__ void __launch_bounds__(256) k_gate_amp(const int16_t *__restrict__ x, const int64_t *__restrict__ chunk_first,
@@ -1073,12 +1442,31 @@ __global__ void __launch_bounds__(256) k_gate_amp(const int16_t *__restrict__ x,
         const int mid = (a + b) >> 1;
         if (chunk_first[mid] <= gw) a = mid; else b = mid;
     }
-    const int16_t *src = x + off[a] + (gw - chunk_first[a]) * AFSK_GATE_CHUNK;
-    uint32_t sum = 0;
-    for (int i = lane; i < AFSK_GATE_CHUNK; i += 32) {
-        const int v = src[i];
-        sum += (uint32_t)(v < 0 ? -v : v);
+    // the chunk as 16-byte vectors from the aligned address at or below its first frame: 256 vectors,
+    // or 257 with the frames outside the chunk masked off when it starts mid-vector
+    const long long g0 = off[a] + (gw - chunk_first[a]) * AFSK_GATE_CHUNK;
+    const int e = (int)(g0 & 7);
+    const uint4 *src = reinterpret_cast<const uint4 *>(x + (g0 - e));
+    const int nvec = AFSK_GATE_CHUNK / 8 + (e ? 1 : 0);
+    int acc = 0;
+    for (int v = lane; v < nvec; v += 32) {
+        const uint4 qv = ld_nc_v4(src + v);
+        // sign(x) per frame as a signed byte (+1 / -1), zero outside [g0, g0 + 2048): sum sign(x) * x = sum |x|
+        uint32_t sa = prmt(qv.x, qv.y, 0xFDB9u) | 0x01010101u, sb = prmt(qv.z, qv.w, 0xFDB9u) | 0x01010101u;
+        if (v == 0 && e) {
+            const unsigned long long keep = ~0ull << (8 * e);
+            sa &= (uint32_t)keep; sb &= (uint32_t)(keep >> 32);
+        }
+        if (v == AFSK_GATE_CHUNK / 8) {          // only reached when e > 0: frames 0 .. e-1 of the last vector
+            const unsigned long long keep = ~(~0ull << (8 * e));
+            sa &= (uint32_t)keep; sb &= (uint32_t)(keep >> 32);
+        }
+        acc = __dp2a_lo((int)qv.x, (int)sa, acc);
+        acc = __dp2a_hi((int)qv.y, (int)sa, acc);
+        acc = __dp2a_lo((int)qv.z, (int)sb, acc);
+        acc = __dp2a_hi((int)qv.w, (int)sb, acc);
     }
+    uint32_t sum = (uint32_t)acc;             // <= 2048 * 32768 = 2^26
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
     if (lane == 0) amp[gw] = (int32_t)(sum / AFSK_GATE_CHUNK);          // getAmplitude :94-98
@@ -1201,6 +1589,9 @@ static cudaError_t demod_set_smem_attr()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small_v1<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small_v1<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small_v1<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 #define X(NT, MG) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod<NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     AFSK_DEMOD_VARIANTS(X)
@@ -1234,6 +1625,7 @@ struct AfskRxPlan {
     int64_t sum_windows = 0;      // over the captures decoded on the GPU
     int64_t gpu_caps = 0;
     bool timing = false;
+    bool small_v1 = false, clock_v1 = false, frame_v1 = false;   // A/B switches (environment, read at plan creation)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
 
@@ -1249,7 +1641,7 @@ static size_t demod_smem_bytes(const Group &g)
     if (g.shift_wpt)
         return (size_t)g.stages * g.stage_bytes + kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t);
     if (g.small_wpt)
-        return (size_t)g.stages * g.stage_bytes + (size_t)8 * (g.bf / 8 + 1) * 16 + kMaxStages * sizeof(TileMeta) +
+        return (size_t)g.stages * g.stage_bytes + (size_t)8 * (2 * (g.bf / 8) + 1) * 16 + kMaxStages * sizeof(TileMeta) +
                2 * kMaxStages * sizeof(uint64_t);
     return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * (8 * (2 * g.nt + 1) + 1) * 16 +
            kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t) + 2 * kConsumerThreads;
@@ -1317,6 +1709,46 @@ static bool configure_group(Group &g, int bf)
     return g.smem <= 227 * 1024;
 }
 
+// scratch of one gate call: freed on every exit path
+struct GateScratch {
+    int64_t *d_first = nullptr, *d_off = nullptr;
+    int32_t *d_amp = nullptr;
+    ~GateScratch() { cudaFree(d_first); cudaFree(d_off); cudaFree(d_amp); }
+};
+
+// chunk amplitudes of S streams, then one open/close search (max_calls < 0, k_gate_scan) or the walk
+// of successive receive() calls (k_gate_multi)
+static int gate_run(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start, int amp_end,
+                    int64_t timeout_frames, int max_calls, int64_t *d_ranges, int32_t *d_counts, void *stream)
+{
+    if (S == 0) return AFSK_OK;
+    if ((reinterpret_cast<uintptr_t>(d_samples) & 15) != 0) { afsk_set_error("gate: d_samples must be 16-byte aligned"); return AFSK_E_ARG; }
+    AfskDeviceGuard guard(device);
+    if (!guard.ok) { afsk_set_error("cannot select device %d", device); return AFSK_E_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int64_t> first((size_t)S + 1, 0);
+    for (int s = 0; s < S; s++) {
+        if (h_offsets[s + 1] < h_offsets[s] || h_offsets[s] < 0) { afsk_set_error("gate: offsets must be non-negative and non-decreasing"); return AFSK_E_ARG; }
+        first[s + 1] = first[s] + (h_offsets[s + 1] - h_offsets[s]) / AFSK_GATE_CHUNK;
+    }
+    const long long total = first[S];
+    GateScratch g;
+    AFSK_CUDA(cudaMalloc((void **)&g.d_first, sizeof(int64_t) * ((size_t)S + 1)));
+    AFSK_CUDA(cudaMalloc((void **)&g.d_off, sizeof(int64_t) * ((size_t)S + 1)));
+    AFSK_CUDA(cudaMalloc((void **)&g.d_amp, sizeof(int32_t) * (size_t)(total ? total : 1)));
+    AFSK_CUDA(cudaMemcpyAsync(g.d_first, first.data(), sizeof(int64_t) * ((size_t)S + 1), cudaMemcpyHostToDevice, st));
+    AFSK_CUDA(cudaMemcpyAsync(g.d_off, h_offsets, sizeof(int64_t) * ((size_t)S + 1), cudaMemcpyHostToDevice, st));
+    if (total > 0) {
+        const int wpb = 8;
+        k_gate_amp<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_samples, g.d_first, g.d_off, S, total, g.d_amp);
+    }
+    if (max_calls < 0) k_gate_scan<<<S, kFrameThreads, 0, st>>>(g.d_amp, g.d_first, amp_start, amp_end, timeout_frames, d_ranges);
+    else k_gate_multi<<<S, 32, 0, st>>>(g.d_amp, g.d_first, amp_start, amp_end, timeout_frames, max_calls, d_ranges, d_counts);
+    AFSK_CUDA(cudaGetLastError());
+    AFSK_CUDA(cudaStreamSynchronize(st));     // the host staging vector and the scratch go out of scope
+    return AFSK_OK;
+}
+
 extern "C" {
 
 int64_t afsk_rx_out_capacity(int64_t n_samples, int baud)
@@ -1351,6 +1783,10 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     if (!P) return AFSK_E_ARG;
     P->device = device;
     P->B = B;
+    auto env_on = [](const char *name) { const char *v = getenv(name); return v && atoi(v) != 0; };
+    P->small_v1 = env_on("AFSK_SMALL_V1");
+    P->clock_v1 = env_on("AFSK_CLOCK_V1");
+    P->frame_v1 = env_on("AFSK_FRAME_V1");
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) P->sm_count = sms;
     P->caps.resize(B);
@@ -1505,7 +1941,8 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     AfskDeviceGuard guard(P->device);
     if (!guard.ok) { afsk_set_error("cannot select device %d", P->device); return AFSK_E_CUDA; }
     cudaStream_t st = (cudaStream_t)stream;
-    k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
+    if (P->clock_v1) k_clock<true><<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
+    else k_clock<false><<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
     for (const Group &g : P->groups) {
         DemodParams p;
         p.samples = d_samples; p.caps = P->d_caps; p.clock = P->d_clock;
@@ -1522,7 +1959,11 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        if (g.small_wpt && g.bf == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        const bool small_v1 = P->small_v1;
+        if (g.small_wpt && small_v1 && g.bf == 8) k_demod_small_v1<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && small_v1 && g.bf == 16) k_demod_small_v1<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && small_v1 && g.bf == 24) k_demod_small_v1<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.small_wpt && g.bf == 16) k_demod_small<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.small_wpt && g.bf == 24) k_demod_small<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
@@ -1533,7 +1974,10 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
             P->timing_events.emplace_back(e0, e1);
         }
     }
-    if (P->max_windows >= ((int64_t)1 << 30))
+    if (P->max_windows <= kFrameWarpMaxWindows && !P->frame_v1)
+        k_frame_warp<<<(P->B + kFrameWarpCaps - 1) / kFrameWarpCaps, 32 * kFrameWarpCaps, 0, st>>>(P->d_caps, P->d_clock, P->d_planes,
+                                                                                                 d_out, d_res, P->B);
+    else if (P->max_windows >= ((int64_t)1 << 30))
         k_frame<512, 8, long long><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     else if (P->sum_windows > 65536 * std::max<int64_t>(P->gpu_caps, 1))   // long captures on average
         k_frame<512, 8, int><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
@@ -1589,59 +2033,18 @@ int afsk_rx_decode_host(int device, const int16_t *h_samples, const int64_t *h_o
 int afsk_rx_gate(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start, int amp_end,
                  int64_t timeout_frames, int64_t *d_range, void *stream)
 {
-    if (S < 0 || (S > 0 && (!d_samples || !h_offsets || !d_range))) return AFSK_E_ARG;
-    if (S == 0) return AFSK_OK;
-    AfskDeviceGuard guard(device);
-    if (!guard.ok) return AFSK_E_CUDA;
-    cudaStream_t st = (cudaStream_t)stream;
-    std::vector<int64_t> first(S + 1, 0);
-    for (int s = 0; s < S; s++) first[s + 1] = first[s] + (h_offsets[s + 1] - h_offsets[s]) / AFSK_GATE_CHUNK;
-    const long long total = first[S];
-    int64_t *d_first = nullptr, *d_off = nullptr;
-    int32_t *d_amp = nullptr;
-    AFSK_CUDA(cudaMalloc((void **)&d_first, sizeof(int64_t) * (S + 1)));
-    AFSK_CUDA(cudaMalloc((void **)&d_off, sizeof(int64_t) * (S + 1)));
-    AFSK_CUDA(cudaMalloc((void **)&d_amp, sizeof(int32_t) * (total ? total : 1)));
-    AFSK_CUDA(cudaMemcpyAsync(d_first, first.data(), sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
-    AFSK_CUDA(cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
-    if (total > 0) {
-        const int wpb = 8;
-        k_gate_amp<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_samples, d_first, d_off, S, total, d_amp);
-    }
-    k_gate_scan<<<S, kFrameThreads, 0, st>>>(d_amp, d_first, amp_start, amp_end, timeout_frames, d_range);
-    AFSK_CUDA(cudaGetLastError());
-    AFSK_CUDA(cudaStreamSynchronize(st));     // host staging vectors go out of scope
-    cudaFree(d_first); cudaFree(d_off); cudaFree(d_amp);
-    return AFSK_OK;
+    if (S < 0 || (S > 0 && (!d_samples || !h_offsets || !d_range))) { afsk_set_error("afsk_rx_gate: bad argument"); return AFSK_E_ARG; }
+    return gate_run(device, d_samples, h_offsets, S, amp_start, amp_end, timeout_frames, -1, d_range, nullptr, stream);
 }
 
 int afsk_rx_gate_multi(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start, int amp_end,
                        int64_t timeout_frames, int max_calls, int64_t *d_ranges, int32_t *d_counts, void *stream)
 {
-    if (S < 0 || max_calls < 0 || (S > 0 && (!d_samples || !h_offsets || !d_ranges || !d_counts))) return AFSK_E_ARG;
-    if (S == 0) return AFSK_OK;
-    AfskDeviceGuard guard(device);
-    if (!guard.ok) return AFSK_E_CUDA;
-    cudaStream_t st = (cudaStream_t)stream;
-    std::vector<int64_t> first(S + 1, 0);
-    for (int s = 0; s < S; s++) first[s + 1] = first[s] + (h_offsets[s + 1] - h_offsets[s]) / AFSK_GATE_CHUNK;
-    const long long total = first[S];
-    int64_t *d_first = nullptr, *d_off = nullptr;
-    int32_t *d_amp = nullptr;
-    AFSK_CUDA(cudaMalloc((void **)&d_first, sizeof(int64_t) * (S + 1)));
-    AFSK_CUDA(cudaMalloc((void **)&d_off, sizeof(int64_t) * (S + 1)));
-    AFSK_CUDA(cudaMalloc((void **)&d_amp, sizeof(int32_t) * (total ? total : 1)));
-    AFSK_CUDA(cudaMemcpyAsync(d_first, first.data(), sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
-    AFSK_CUDA(cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
-    if (total > 0) {
-        const int wpb = 8;
-        k_gate_amp<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_samples, d_first, d_off, S, total, d_amp);
+    if (S < 0 || max_calls < 0 || (S > 0 && (!d_samples || !h_offsets || !d_ranges || !d_counts))) {
+        afsk_set_error("afsk_rx_gate_multi: bad argument");
+        return AFSK_E_ARG;
     }
-    k_gate_multi<<<S, 32, 0, st>>>(d_amp, d_first, amp_start, amp_end, timeout_frames, max_calls, d_ranges, d_counts);
-    AFSK_CUDA(cudaGetLastError());
-    AFSK_CUDA(cudaStreamSynchronize(st));     // host staging vectors go out of scope
-    cudaFree(d_first); cudaFree(d_off); cudaFree(d_amp);
-    return AFSK_OK;
+    return gate_run(device, d_samples, h_offsets, S, amp_start, amp_end, timeout_frames, max_calls, d_ranges, d_counts, stream);
 }
 
 }  // extern "C"

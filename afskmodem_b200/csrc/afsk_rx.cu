@@ -4,8 +4,9 @@
 // captures with three kernels:
 //
 //   k_clock   __recoverClockIndex (:322-339): first 4096 frames -> prefix sum in shared memory,
-//             every candidate offset scored from 7 prefix look-ups (closed form of getDiff
-//             against the +/-full-scale training cycle), block arg-min with first-index ties.
+//             every candidate offset scored from 7 prefix taps (closed form of getDiff against
+//             the +/-full-scale training cycle) kept in registers along chains of candidates a
+//             quarter bit apart, block arg-min with first-index ties.
 //   k_demod   __decodeBit (:342-351) + __amplify (:287-296) + getAmplitude (:94-98) for EVERY
 //             bit window of every capture: the streaming, HBM-bound kernel.  Persistent CTAs,
 //             1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a multi-stage shared-memory ring
@@ -13,7 +14,8 @@
 //             vectors and reduce each window to a mark/space decision bit and a "quiet" bit with
 //             packed 16x2 integer ops and IDP.2A dot products.  Output: 2 bits per window.
 //   k_frame   __scanTraining (:386-390) terminator search, the data loop's end detector (:372-378),
-//             ECC.decode (:154-163) and __bitsToBytes (:393-399) on the packed bit planes.
+//             ECC.decode (:154-163) and __bitsToBytes (:393-399) on the packed bit planes
+//             (k_frame_warp: one warp per capture; k_frame: one CTA per capture for very long ones).
 //
 // All arithmetic is integer and bit-exact with the reference (see DESIGN.md for the algebra).
 #include <stdlib.h>
@@ -86,7 +88,6 @@ __device__ __forceinline__ long long num_windows(long long n, int bf, int clk)
 }
 
 // ------------------------------------------------------------------------------ k_clock ----
-template <bool kV1>
 __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restrict__ x,
                                                          const CapDesc *__restrict__ caps,
                                                          int32_t *__restrict__ clock,
@@ -163,57 +164,6 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     }
     __syncthreads();
 
-    if constexpr (kV1) {   // previous candidate loop (seven taps per candidate), kept for the same-box A/B
-        const int bf = d.bf, q = bf >> 2, h = bf >> 1;
-        const int span = AFSK_SYNC_FRAMES - 2 * bf;                 // :327
-        const uint32_t c0 = 65535u * (uint32_t)bf;
-        const uint32_t div = 2u * (uint32_t)bf;
-        // getDiff(i) = floor(D_i / 2bf) is monotone in D_i, so the first strict minimum (:332-337) is the
-        // first i with D_i <= T where T = (floor(min D / 2bf) + 1) * 2bf - 1: one division per capture.
-        constexpr int kPerThread = AFSK_SYNC_FRAMES / kClockThreads;   // 32 candidates per thread at most
-        uint32_t Dv[kPerThread];
-        uint32_t best = 0xFFFFFFFFu;
-        // seven prefix taps per candidate, candidate i = tid + 128 k (conflict-free: consecutive lanes,
-        // consecutive words); the last partial round reads up to 127 words past the scanned range
-        // (inside Qs, values unused)
-        const uint32_t *p0 = P + tid + e, *p1 = p0 + q, *p2 = p0 + 2 * q, *p3 = p0 + 3 * q, *p4 = p0 + bf,
-                       *p5 = p0 + bf + h, *p6 = p0 + 2 * bf;
-        const int kmax = (span + kClockThreads - 1) / kClockThreads;
-    #pragma unroll
-        for (int k = 0; k < kPerThread; k++) {
-            uint32_t D = 0xFFFFFFFFu;
-            if (k < kmax) {
-                const int o = k * kClockThreads;
-                // sum_j |T[j] - x[i+j]| over the training cycle (mark: q HI,q LO,q HI,q LO ; space: h HI,h LO)
-                D = c0 + p0[o] + p6[o] - 2u * (p1[o] - p2[o] + p3[o] - p4[o] + p5[o]);
-                D = (tid + o < span) ? D : 0xFFFFFFFFu;
-            }
-            Dv[k] = D;
-            best = min(best, D);
-        }
-    #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
-        if (lane == 0) warp_min[warp] = best;
-        __syncthreads();
-        best = warp_min[0];
-    #pragma unroll
-        for (int w = 1; w < kClockThreads / 32; w++) best = min(best, warp_min[w]);
-        const uint32_t T = (best / div + 1u) * div - 1u;            // getDiff :107
-        uint32_t first = 0xFFFFFFFFu;
-    #pragma unroll
-        for (int k = kPerThread - 1; k >= 0; k--)
-            if (Dv[k] <= T) first = (uint32_t)(tid + k * kClockThreads);
-    #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
-        __syncthreads();
-        if (lane == 0) warp_min[warp] = first;
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < kClockThreads / 32; w++) first = min(first, warp_min[w]);
-            clock[c] = (int32_t)first;
-        }
-        return;
-    } else {
     const int bf = d.bf, q = bf >> 2;
     const int span = AFSK_SYNC_FRAMES - 2 * bf;                 // :327
     const uint32_t c0 = 65535u * (uint32_t)bf;
@@ -293,7 +243,6 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     if (tid == 0) {
         for (int w = 1; w < kClockThreads / 32; w++) first = min(first, warp_min[w]);
         clock[c] = (int32_t)first;
-    }
     }
 }
 
@@ -935,127 +884,6 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodPar
     }
 }
 
-// ---- k_demod_small_v1: previous version, kept for the same-box A/B (AFSK_SMALL_V1=1) ----
-// Short windows (bf = 8, 16, 24: 6000 / 3000 / 2000 baud): one thread decodes kWpt consecutive
-// windows of kM vectors each, so the per-tile bookkeeping is paid once per 48-64 samples instead of
-// once per 8-24.  Every vector is re-aligned to the window grid with 4 PRMTs (slots >= e from
-// vector i, slots < e from vector i+1), the +/-1 weights are uniform over the tile (alignment e is
-// per tile) and live in registers, and threads visit their windows in a lane-rotated order so that
-// the 128-bit shared-memory loads of a warp fall in different banks.
-template <int kM, int kWpt>
-__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small_v1(const DemodParams p)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int S = p.stages;
-    uint8_t *stage_base = smem;
-    uint4 *wtab = reinterpret_cast<uint4 *>(smem + (size_t)S * p.stage_bytes);     // [8 alignments][kM + 1]
-    TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + 8 * (kM + 1));
-    uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
-    uint64_t *empty = full + kMaxStages;
-    constexpr int kBf = 8 * kM, kSeg = kBf * kWpt, kLanesPerWord = 32 / kWpt;
-
-    // weights of re-aligned vector i at alignment e: slot s holds window sample 8i + ((s - e) mod 8);
-    // entry kM holds the 4 PRMT selectors
-    if (tid < 8 * (kM + 1)) {
-        const int e = tid / (kM + 1), i = tid % (kM + 1);
-        if (i < kM) {
-            const int q = kBf >> 2;
-            uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u};
-#pragma unroll
-            for (int sl = 0; sl < 8; sl++) {
-                const int r = 8 * i + ((sl - e + 8) & 7), qd = r / q, sh = 8 * (sl & 3);
-                mk[sl >> 2] |= ((qd & 1) ? 0xFFu : 0x01u) << sh;
-                sp[sl >> 2] |= ((qd & 2) ? 0xFFu : 0x01u) << sh;
-            }
-            wtab[tid] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
-        } else {
-            uint32_t sel[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) sel[j] = (2 * j >= e) ? 0x3210u : ((2 * j + 1 < e) ? 0x7654u : 0x3254u);
-            wtab[tid] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
-        }
-    }
-    if (tid == 0) {
-        for (int s = 0; s < S; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerThreads / 32);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
-    if (ntile <= 0) return;
-    if (warp == kConsumerThreads / 32) {
-        demod_produce(p, ntile, stage_base, meta, full, empty);
-        return;
-    }
-
-    const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int n = 0; n < ntile; ++n) {
-        mbar_wait(&full[s], ph);
-        const TileMeta m = meta[s];
-        uint32_t bits = 0, quiet = 0;
-        if (m.nwin > 0) {
-            const uint4 *wt = wtab + (m.e0 & 7) * (kM + 1);
-            uint4 W[kM];
-#pragma unroll
-            for (int i = 0; i < kM; i++) W[i] = wt[i];
-            const uint4 sel = wt[kM];
-            // kSeg % 8 == 0: the thread's first vector is e0 / 8 + tid * kSeg / 8
-            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) + tid * (kSeg / 8);
-#pragma unroll
-            for (int j = 0; j < kWpt; j++) {
-                const int jj = (j + tid) & (kWpt - 1);           // lane-rotated window order
-                int accM = 0, accS = 0, accA = 0;
-                uint4 cur = dp[jj * kM];
-#pragma unroll
-                for (int i = 0; i < kM; i++) {
-                    const uint4 nxt = dp[jj * kM + i + 1];
-                    const uint32_t x0 = prmt(cur.x, nxt.x, sel.x), x1 = prmt(cur.y, nxt.y, sel.y);
-                    const uint32_t x2 = prmt(cur.z, nxt.z, sel.z), x3 = prmt(cur.w, nxt.w, sel.w);
-                    accum4_full(x0, x1, W[i].x, W[i].z, k512, accM, accS, accA);
-                    accum4_full(x2, x3, W[i].y, W[i].w, k512, accM, accS, accA);
-                    cur = nxt;
-                }
-                // acc = 256 * T.n + T.c with |T.c| <= 24: decide as in k_demod
-                const int Um = (int)((unsigned)accM << 24) >> 24, Us = (int)((unsigned)accS << 24) >> 24;
-                const int du = Um - Us;
-                bool b1 = du > 0;
-                if (du == 0) {
-                    const int Nm = (accM - Um) >> 8, Ns = (accS - Us) >> 8;
-                    if (Ns > Nm) {
-                        const int M2 = 65535 * kBf - 65534 * Um + 2 * Nm;
-                        const int S2 = M2 + 2 * (Ns - Nm);
-                        b1 = (S2 - M2 >= 2 * kBf) || (M2 < (S2 / (2 * kBf)) * (2 * kBf));
-                    }
-                }
-                const bool valid = tid * kWpt + jj < m.nwin;
-                bits |= (uint32_t)(valid && b1) << jj;
-                quiet |= (uint32_t)(valid && (accA < m.thr_bf)) << jj;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (m.nwin > 0) {
-            // kLanesPerWord threads hold the kWpt-bit pieces of one plane word
-            uint32_t bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
-            uint32_t qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
-#pragma unroll
-            for (int o = 1; o < kLanesPerWord; o <<= 1) {
-                bw |= __shfl_xor_sync(0xFFFFFFFFu, bw, o);
-                qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
-            }
-            const int word = (tid * kWpt) >> 5;
-            if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin) p.planes[m.word_base + word] = make_uint2(bw, qw);
-        }
-        if (++s == S) { s = 0; ph ^= 1u; }
-    }
-}
-
 // ------------------------------------------------------------------------ k_demod_shift ----
 // Short windows that are a multiple of 4 but not of 8 samples (bf = 12, 20: 4000 / 2400 baud).  One
 // thread decodes kWpt consecutive windows (kBf * kWpt samples, a multiple of 8).  A window boundary
@@ -1589,9 +1417,6 @@ static cudaError_t demod_set_smem_attr()
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small_v1<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small_v1<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small_v1<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 #define X(NT, MG) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod<NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     AFSK_DEMOD_VARIANTS(X)
@@ -1625,7 +1450,6 @@ struct AfskRxPlan {
     int64_t sum_windows = 0;      // over the captures decoded on the GPU
     int64_t gpu_caps = 0;
     bool timing = false;
-    bool small_v1 = false, clock_v1 = false, frame_v1 = false;   // A/B switches (environment, read at plan creation)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
 
@@ -1783,10 +1607,6 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     if (!P) return AFSK_E_ARG;
     P->device = device;
     P->B = B;
-    auto env_on = [](const char *name) { const char *v = getenv(name); return v && atoi(v) != 0; };
-    P->small_v1 = env_on("AFSK_SMALL_V1");
-    P->clock_v1 = env_on("AFSK_CLOCK_V1");
-    P->frame_v1 = env_on("AFSK_FRAME_V1");
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) P->sm_count = sms;
     P->caps.resize(B);
@@ -1857,6 +1677,8 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
         up((void **)&g.d_tile_gpos, g.tile_gpos.data(), sizeof(int32_t) * g.tile_gpos.size());
         g.tile_gpos.clear(); g.tile_gpos.shrink_to_fit();
         const int total = g.tile_first.back();
+        // two CTAs per SM even where three would fit: measured on one box, 3 CTAs per SM give 6223 GB/s
+        // against 7115 at 1200 baud and 5663 against 6610 at 300 baud (profiles/r1_tuning_log.md)
         const int per_sm = g.smem <= 113 * 1024 ? 2 : 1;
         g.grid = std::max(1, std::min(total, P->sm_count * per_sm));
     }
@@ -1941,8 +1763,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     AfskDeviceGuard guard(P->device);
     if (!guard.ok) { afsk_set_error("cannot select device %d", P->device); return AFSK_E_CUDA; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (P->clock_v1) k_clock<true><<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
-    else k_clock<false><<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
+    k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
     for (const Group &g : P->groups) {
         DemodParams p;
         p.samples = d_samples; p.caps = P->d_caps; p.clock = P->d_clock;
@@ -1954,16 +1775,12 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         // L2 evict-first on the bulk copies (the samples are read once).  Same-box A/B: k_demod +2-6 %
         // (c2 0.768 -> 0.745 ms, 600 baud 0.819 -> 0.770), k_demod_shift +1-2.5 %, k_demod_small 0 to -10 %
         // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 forces.
-        static const int l2_force = getenv("AFSK_L2_HINT") ? atoi(getenv("AFSK_L2_HINT")) : -1;
+        const int l2_force = getenv("AFSK_L2_HINT") ? atoi(getenv("AFSK_L2_HINT")) : -1;
         p.l2_hint = l2_force >= 0 ? l2_force : (g.small_wpt ? 0 : 1);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        const bool small_v1 = P->small_v1;
-        if (g.small_wpt && small_v1 && g.bf == 8) k_demod_small_v1<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && small_v1 && g.bf == 16) k_demod_small_v1<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && small_v1 && g.bf == 24) k_demod_small_v1<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        if (g.small_wpt && g.bf == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.small_wpt && g.bf == 16) k_demod_small<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.small_wpt && g.bf == 24) k_demod_small<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
@@ -1974,7 +1791,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
             P->timing_events.emplace_back(e0, e1);
         }
     }
-    if (P->max_windows <= kFrameWarpMaxWindows && !P->frame_v1)
+    if (P->max_windows <= kFrameWarpMaxWindows)
         k_frame_warp<<<(P->B + kFrameWarpCaps - 1) / kFrameWarpCaps, 32 * kFrameWarpCaps, 0, st>>>(P->d_caps, P->d_clock, P->d_planes,
                                                                                                  d_out, d_res, P->B);
     else if (P->max_windows >= ((int64_t)1 << 30))

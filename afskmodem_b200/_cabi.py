@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libafsk_b200.so")
+# AFSK_LIB_PATH: a differently built copy of the library, for same-box A/B runs of compile-time variants
+LIB_PATH = os.environ.get("AFSK_LIB_PATH") or os.path.join(_HERE, "libafsk_b200.so")
 
 AFSK_OK, AFSK_E_ARG, AFSK_E_CUDA, AFSK_E_BAUD, AFSK_E_UNSUPPORTED = 0, -1, -2, -3, -4
 ST_OK, ST_NO_CLOCK, ST_NO_DATA = 0, 1, 2

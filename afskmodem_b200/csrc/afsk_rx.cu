@@ -1171,14 +1171,14 @@ __global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDes
     __syncthreads();
     const int c = blockIdx.x * kFrameWarpCaps + (tid >> 5);
     if (c >= B) return;
+    const int clk = clock[c];                          // issued together with the descriptor load
     const CapDesc d = caps[c];
     if (d.status0 != 0) return;
-    const int clk = clock[c];
     const int K = (int)num_windows(d.n, d.bf, clk);
     const int nwords = (K + 31) >> 5;
     const uint2 *PL = planes + d.plane_base;
     constexpr unsigned NONE = 0x7FFFFFFFu;
-    constexpr int kWords = 4;                           // plane words per lane per step
+    constexpr int kWords = 8;                           // plane words per lane per step (loads in flight)
 
     // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
     unsigned kterm = NONE;
@@ -1225,6 +1225,7 @@ __global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDes
     uint8_t *o = out + d.out_off;                    // 16-byte aligned
     // four bytes (56 coded bits) per lane step: three plane words, one 32-bit store
     const int nquad = nbytes >> 2;
+#pragma unroll 2
     for (int i = lane; i < nquad; i += 32) {
         const int pos = k0 + 56 * i;
         const int wi = pos >> 5;

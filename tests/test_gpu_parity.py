@@ -245,6 +245,33 @@ def test_listen_gate_golden():
             assert b // 2048 == g["reads"]
 
 
+def test_listen_gate_streams_at_every_alignment():
+    """Several recorded streams in one call whose first frames fall on every 16-byte phase (the chunk
+    amplitudes are summed from 128-bit vectors with the frames outside a chunk masked off), full-scale
+    negative samples included (|-32768| = 32768 must not wrap)."""
+    rng = np.random.default_rng(77)
+    streams = []
+    for i in range(24):
+        n = int(rng.integers(3, 9)) * 2048 + int(rng.integers(0, 2048)) + (i % 8 == 0) * 1   # ragged tails, odd lengths
+        level = int(rng.choice([300, 9000, 15000, 19000, 32768]))
+        x = rng.integers(-level, level, n).astype(np.int32)
+        x[: int(rng.integers(1, 3)) * 2048] //= 64                      # quiet start, so that the gate opens later
+        x[int(rng.integers(0, n))] = -32768
+        if i % 5 == 0:
+            x[2048:4096] = -32768                                       # a whole chunk at full-scale negative
+        streams.append(np.clip(x, -32768, 32767).astype(np.int16))
+    streams.append(np.zeros(2047, np.int16))                            # no full chunk at all
+    streams.append(np.zeros(0, np.int16))
+    r = A.Receiver(1200, 6000, 4000)            # mean |x| of the noise is level / 2
+    opened = 0
+    for timeout in (0.0, 0.05, 1.0):
+        got = r.listen_gate(streams, timeout)
+        want = [O.listen_gate(s, 6000, 4000, int(timeout * 48000)) for s in streams]
+        assert got == want, timeout
+        opened += sum(1 for g in got if g[0])
+    assert opened >= 10                          # the comparison is not vacuous
+
+
 @pytest.mark.parametrize("g", load_gate_multi_golden(), ids=[g["name"] for g in load_gate_multi_golden()])
 def test_receive_all_matches_successive_reference_receives(g):
     """Recorded stream with several transmissions: gate on the GPU, all recordings decoded as one

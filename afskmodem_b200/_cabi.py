@@ -22,7 +22,7 @@ ST_EXC_WAVELEN, ST_EXC_INDEX, ST_EXC_BAUD = -1, -2, -3
 SYMBOLS = [
     "afsk_abi_version", "afsk_last_error", "afsk_device_count", "afsk_device_info", "afsk_malloc",
     "afsk_free", "afsk_host_alloc", "afsk_host_free", "afsk_memcpy_h2d", "afsk_memcpy_d2h",
-    "afsk_memset", "afsk_stream_create", "afsk_stream_destroy", "afsk_stream_sync",
+    "afsk_memset", "afsk_stream_create", "afsk_stream_destroy", "afsk_stream_sync", "afsk_stream_wait_stream",
     "afsk_tone_lengths", "afsk_rx_plan_create", "afsk_rx_plan_create_ranges", "afsk_rx_plan_destroy", "afsk_rx_plan_out_offsets",
     "afsk_rx_plan_launches", "afsk_rx_plan_set_timing", "afsk_rx_plan_demod_time", "afsk_rx_decode", "afsk_rx_plan_planes", "afsk_rx_decode_host",
     "afsk_rx_out_capacity", "afsk_rx_gate", "afsk_rx_gate_multi", "afsk_tx_num_samples", "afsk_tx_plan_create",
@@ -74,6 +74,7 @@ def lib():
     L.afsk_stream_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.afsk_stream_destroy.argtypes = [C.c_int, vp]
     L.afsk_stream_sync.argtypes = [C.c_int, vp]
+    L.afsk_stream_wait_stream.argtypes = [C.c_int, vp, vp]
     L.afsk_tone_lengths.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.afsk_rx_plan_create.argtypes = [C.c_int, C.c_int, i64p, i32p, i32p, C.POINTER(vp)]
     L.afsk_rx_plan_create_ranges.argtypes = [C.c_int, C.c_int, i64p, i64p, i32p, i32p, C.POINTER(vp)]
@@ -186,6 +187,20 @@ def c_paths(filenames):
 
 def stream_sync(device: int, stream=None):
     check(lib().afsk_stream_sync(device, C.c_void_p(stream or 0)))
+
+
+def stream_create(device: int) -> int:
+    s = C.c_void_p()
+    check(lib().afsk_stream_create(device, C.byref(s)))
+    return s.value
+
+
+def stream_destroy(device: int, stream: int):
+    lib().afsk_stream_destroy(device, C.c_void_p(stream))
+
+
+def stream_wait_stream(device: int, waiter: int, signaller: int):
+    check(lib().afsk_stream_wait_stream(device, C.c_void_p(waiter), C.c_void_p(signaller)))
 
 
 def tone_lengths(baud: int):

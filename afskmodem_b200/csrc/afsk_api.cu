@@ -112,6 +112,19 @@ int afsk_stream_destroy(int device, void *stream)
     return AFSK_OK;
 }
 
+int afsk_stream_wait_stream(int device, void *waiter, void *signaller)
+{
+    AfskDeviceGuard g(device);
+    if (!g.ok) return AFSK_E_CUDA;
+    cudaEvent_t ev;
+    AFSK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, (cudaStream_t)signaller);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)waiter, ev, 0);
+    cudaEventDestroy(ev);                    // released once the recorded work has completed
+    if (e != cudaSuccess) { afsk_set_error("afsk_stream_wait_stream: %s", cudaGetErrorString(e)); return AFSK_E_CUDA; }
+    return AFSK_OK;
+}
+
 int afsk_stream_sync(int device, void *stream)
 {
     AfskDeviceGuard g(device);

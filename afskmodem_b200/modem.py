@@ -132,6 +132,10 @@ def _as_int_threshold(t) -> int:
 
 
 # ------------------------------------------------------------------------------ receiver ----
+PIPELINE_MIN_BYTES = 64 << 20      # decode_batch overlaps copy and kernels from this batch size on
+PIPELINE_CHUNKS = 8
+
+
 class RxBatch:
     """Decoded batch: per-capture stage integers (the reference's debug-log values) and payloads."""
 
@@ -246,13 +250,15 @@ class RxSession:
         _cabi.check(_cabi.lib().afsk_rx_plan_demod_time(self.plan, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def download(self, stream=None, res_host: np.ndarray | None = None, blob_host: np.ndarray | None = None) -> RxBatch:
+    def download(self, stream=None, res_host: np.ndarray | None = None, blob_host: np.ndarray | None = None,
+                 sync: bool = True) -> RxBatch:
         res = res_host if res_host is not None else np.zeros(self.B, dtype=_cabi.RX_RESULT_DTYPE)
         blob = blob_host if blob_host is not None else np.zeros(int(self.out_off[-1]), dtype=np.uint8)
         if self.B:
             self.d_res.download(res, stream)
             self.d_out.download(blob, stream)
-        _cabi.stream_sync(self.device, stream)
+        if sync:
+            _cabi.stream_sync(self.device, stream)
         return RxBatch(res, blob, self.out_off)
 
     def planes(self, capture: int):
@@ -268,6 +274,83 @@ class RxSession:
         unpack = lambda col: np.unpackbits(np.ascontiguousarray(words[:, col]).view(np.uint8),  # noqa: E731
                                            bitorder="little")[:mw.value].astype(bool)
         return unpack(0), unpack(1)
+
+
+class PipelinedRxSession:
+    """Host-buffer decode of a large batch with the PCIe copy and the kernels overlapped.
+
+    The batch is cut into ``chunks`` contiguous capture ranges of about equal size in samples
+    (``shard.shard_captures``), each with its own plan over the SAME device sample buffer (the plans
+    keep the batch's absolute offsets).  A copy stream uploads range after range; the compute stream
+    waits for range j's copy (``afsk_stream_wait_stream``) and decodes it while range j+1 is on the
+    link, so the call costs the H2D time plus the LAST range's kernels instead of H2D plus all of them.
+    Results land in one RxBatch exactly as from a single plan."""
+
+    def __init__(self, offsets, baud, amp_end, device: int, chunks: int):
+        from .shard import shard_captures
+        self.device = device
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.B = len(self.offsets) - 1
+        self.total_samples = int(self.offsets[-1])
+        baud = np.ascontiguousarray(np.broadcast_to(np.asarray(baud, dtype=np.int32), (self.B,)))
+        amp_end = np.ascontiguousarray(np.broadcast_to(np.asarray(amp_end, dtype=np.int32), (self.B,)))
+        self.ranges = [(lo, hi) for lo, hi in shard_captures(np.diff(self.offsets), chunks) if hi > lo]
+        self.sessions = [RxSession(self.offsets[lo:hi + 1], baud[lo:hi], amp_end[lo:hi], device) for lo, hi in self.ranges]
+        self.d_samples = DeviceBuffer(device, (self.total_samples * 2 + 15) // 16 * 16 + 16)
+        for sess in self.sessions:
+            sess.bind(self.d_samples.ptr)
+        self.copy_stream = _cabi.stream_create(device)
+        self.compute_stream = _cabi.stream_create(device)
+        self.launches = sum(sess.launches for sess in self.sessions)
+        # one host result set for the whole batch; every range downloads into its slice
+        self.res_lo = np.cumsum([0] + [sess.B for sess in self.sessions])
+        self.blob_lo = np.cumsum([0] + [int(sess.out_off[-1]) for sess in self.sessions])
+        self.out_off = np.concatenate([sess.out_off[:-1] + self.blob_lo[j] for j, sess in enumerate(self.sessions)] +
+                                      [self.blob_lo[-1:]]).astype(np.int64)
+        # two pinned host result sets, used alternately: the D2H copies are truly asynchronous (range j's
+        # results travel while range j+1 is still uploading — the link is full duplex) and the batch a call
+        # returns stays valid until the call after the next one
+        self._host = [(_cabi.PinnedArray((self.B,), _cabi.RX_RESULT_DTYPE),
+                       _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8)) for _ in range(2)]
+        self._flip = 0
+        _cabi.stream_sync(device)          # plan set-up (default stream) is complete before the side streams run
+
+    def decode(self, samples: np.ndarray) -> RxBatch:
+        """The returned batch views pinned memory owned by this session: it is overwritten by the second
+        decode after this one (copy what must live longer)."""
+        samples = np.ascontiguousarray(samples, dtype=np.int16)
+        assert len(samples) >= self.total_samples
+        owner = self._host[self._flip]
+        res, blob = (h.array for h in owner)
+        self._flip ^= 1
+        for j, ((lo, hi), sess) in enumerate(zip(self.ranges, self.sessions)):
+            a, b = int(self.offsets[lo]), int(self.offsets[hi])
+            if b > a:
+                self.d_samples.upload(samples[a:b], self.copy_stream, offset=2 * a)
+            _cabi.stream_wait_stream(self.device, self.compute_stream, self.copy_stream)
+            sess.run(self.compute_stream)
+            sess.download(self.compute_stream, res[self.res_lo[j]:self.res_lo[j + 1]],
+                          blob[self.blob_lo[j]:self.blob_lo[j + 1]], sync=False)
+        _cabi.stream_sync(self.device, self.compute_stream)
+        out = RxBatch(res, blob[:int(self.blob_lo[-1])], self.out_off)
+        out._owner = owner                 # the pinned memory lives as long as a batch refers to it
+        return out
+
+    def close(self):
+        for sess in getattr(self, "sessions", []):
+            sess.close()
+        self.sessions = []
+        if getattr(self, "d_samples", None) is not None:
+            self.d_samples.close()
+            self.d_samples = None
+        for name in ("copy_stream", "compute_stream"):
+            st = getattr(self, name, None)
+            if st:
+                _cabi.stream_destroy(self.device, st)
+                setattr(self, name, None)
+        self._host = []                    # freed when the last RxBatch viewing them is gone
+
+    __del__ = close
 
 
 def _concat(captures):
@@ -364,18 +447,19 @@ class Receiver:
         self._log = Log("afskmodem.Receiver")
         self._cache = None                                       # (key, RxSession) of the last batch layout
 
-    def _session(self, offsets: np.ndarray, dev: int, baud=None, amp_end=None) -> RxSession:
+    def _session(self, offsets: np.ndarray, dev: int, baud=None, amp_end=None, chunks: int = 1):
         """Plan + device buffers are kept between calls with the same batch layout (like an FFT
-        plan cache): repeated decode_batch calls then pay only H2D, kernels and D2H."""
+        plan cache): repeated decode_batch calls then pay only H2D, kernels and D2H.
+        chunks > 1: a PipelinedRxSession (copy / compute overlap over capture ranges)."""
         baud = self._baud if baud is None else np.ascontiguousarray(baud, dtype=np.int32)
         amp_end = _as_int_threshold(self._amp_end) if amp_end is None else \
             np.ceil(np.asarray(amp_end, dtype=np.float64)).astype(np.int32)
-        key = (dev, baud if np.isscalar(baud) else baud.tobytes(), amp_end if np.isscalar(amp_end) else amp_end.tobytes(),
-               offsets.tobytes())
+        key = (dev, chunks, baud if np.isscalar(baud) else baud.tobytes(),
+               amp_end if np.isscalar(amp_end) else amp_end.tobytes(), offsets.tobytes())
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1]
         self.close()
-        s = RxSession(offsets, baud, amp_end, dev)
+        s = RxSession(offsets, baud, amp_end, dev) if chunks <= 1 else PipelinedRxSession(offsets, baud, amp_end, dev, chunks)
         self._cache = (key, s)
         return s
 
@@ -396,15 +480,26 @@ class Receiver:
 
     # -- batch API -------------------------------------------------------------------------
     def decode_batch(self, samples, offsets=None, device: int | None = None, baud_rate=None,
-                     amp_end_threshold=None) -> RxBatch:
+                     amp_end_threshold=None, pipeline: int | None = None) -> RxBatch:
         """Decode B captures.  ``samples``: list of int16 arrays, or one concatenated int16 array
         with ``offsets`` (B+1, in samples).  ``baud_rate`` / ``amp_end_threshold`` (arrays of B) override
-        this receiver's settings per capture for mixed corpora.  Raises the reference's exceptions
-        only through ``to_python``; statuses < 0 mark captures on which ``load`` would raise."""
+        this receiver's settings per capture for mixed corpora.  ``pipeline``: number of capture ranges
+        whose upload and decode are overlapped (None: 8 for batches of 64 MB and more, else 1); a
+        pipelined call returns views of session-owned pinned memory that the second call after it
+        overwrites.
+        Raises the reference's exceptions only through ``to_python``; statuses < 0 mark captures on
+        which ``load`` would raise."""
         if offsets is None:
             samples, offsets = _concat(samples)
         dev = self._device if device is None else device
-        s = self._session(np.ascontiguousarray(offsets, dtype=np.int64), dev, baud_rate, amp_end_threshold)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if pipeline is None:
+            # overlap pays once the copy is much longer than a launch: >= 64 MB of samples, >= 4 captures per range
+            big = len(offsets) > 1 and int(offsets[-1]) * 2 >= PIPELINE_MIN_BYTES
+            pipeline = min(PIPELINE_CHUNKS, (len(offsets) - 1) // 4) if big else 1
+        s = self._session(offsets, dev, baud_rate, amp_end_threshold, chunks=max(int(pipeline), 1))
+        if isinstance(s, PipelinedRxSession):
+            return s.decode(samples)
         s.upload(samples)
         s.run()
         return s.download()

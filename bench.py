@@ -11,8 +11,9 @@ capture.  ~2.47 G samples = 4.9 GB of int16 per GPU: larger tha
 is needed between timed iterations.  A step = one decode of the whole batch.
 
   value        decoded Msamples/s, inputs resident in HBM, CUDA events, max over ranks
-  e2e          same metric through Receiver.decode_batch with HOST (pinned) buffers: plan,
-               H2D of all samples, kernels, D2H of results + payloads inside the timed region
+  e2e          same metric through Receiver.decode_batch with HOST (pinned) buffers: H2D of all
+               samples, kernels, D2H of results + payloads inside the timed region (upload and
+               decode overlapped over 8 capture ranges, e2e.h2d_overlapped_ranges)
   roofline     k_demod: 2 bytes/sample x samples per launch / its CUDA-event duration vs the
                measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline the C oracle port of the reference algorithm on the host cores (rank 0, N=1)
@@ -405,6 +406,7 @@ def main():
         e2e = {"value": all_samples / (e2e_ms / 1000) / 1e6, "unit": "Msamples/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": total * 2, "d2h_bytes_per_step": int(32 * B + hb.out_off[-1]),
                "api": "Receiver.decode_batch(pinned int16 samples, offsets, baud_rate=[...], amp_end_threshold=[...])",
+               "h2d_overlapped_ranges": len(getattr(sess_e, "sessions", [None])),
                "steps": args.e2e_steps, "h2d_only_ms": h2d_ms, "h2d_only_gbs": 2.0 * total / h2d_ms / 1e6,
                "share_of_step_in_h2d": h2d_ms / e2e_ms}
         # ---- the same path from wav FILES (Receiver.load_batch: afsk_wav_load host threads -> pinned

@@ -76,6 +76,9 @@ int afsk_memset(int device, void *dst, int value, size_t bytes, void *stream);
 int afsk_stream_create(int device, void **stream);
 int afsk_stream_destroy(int device, void *stream);
 int afsk_stream_sync(int device, void *stream);
+/* everything enqueued on `waiter` after this call runs after everything enqueued on `signaller`
+ * before it (event record + stream wait): lets a copy stream feed a compute stream chunk by chunk */
+int afsk_stream_wait_stream(int device, void *waiter, void *signaller);
 
 /* ---------------------------------------------------------------- tone tables ---------- */
 /* Waveforms.getSpaceTone / getMarkTone lengths (afskmodem.py:68-85) and Receiver.__bit_frames

@@ -288,6 +288,46 @@ def test_receive_all_matches_successive_reference_receives(g):
         assert r.receive_recording(s, g["timeout"], False) == got[0]
 
 
+def test_pipelined_decode_equals_single_plan():
+    """decode_batch(pipeline=K): upload and kernels overlapped over K capture ranges, each with its own
+    plan over the same device buffer — every result field and payload equals the single-plan decode,
+    for K that does and does not divide the batch, with exception / too-short / empty captures mixed in."""
+    rng = np.random.default_rng(2024)
+    caps, bauds, thrs = [], [], []
+    for i in range(37):
+        baud = int(rng.choice([300, 1200, 2400, 4000, 6000, 4800]))
+        fr = O.tx_frames(rng.integers(0, 256, int(rng.integers(1, 60)), dtype=np.uint8).tobytes(),
+                         6000 if baud == 4800 else baud)
+        x = _impair(fr, rng, lead=int(rng.integers(0, 3000)), sigma=float(rng.choice([0, 3000, 9000])))
+        if i % 9 == 4:
+            x = x[:int(rng.integers(0, 4096))]                      # too short for clock recovery (or empty)
+        caps.append(x); bauds.append(baud); thrs.append(int(rng.choice([14000, 9000])))
+    samples, offsets = A.modem._concat(caps)
+    rx = A.Receiver(1200)
+    one = rx.decode_batch(samples, offsets, baud_rate=bauds, amp_end_threshold=thrs, pipeline=1)
+    for k in (2, 3, 8, 37, 64):
+        many = rx.decode_batch(samples, offsets, baud_rate=bauds, amp_end_threshold=thrs, pipeline=k)
+        assert isinstance(rx._cache[1], A.modem.PipelinedRxSession) and len(rx._cache[1].sessions) <= k
+        assert np.array_equal(many.results, one.results), k
+        assert many.payloads() == one.payloads(), k
+    for i, x in enumerate(caps):                                    # and the single plan equals the oracle
+        if bauds[i] == 4800:
+            assert int(one.status[i]) == (_cabi.ST_EXC_WAVELEN if len(x) >= 4096 else _cabi.ST_NO_CLOCK)
+            continue
+        o = O.rx_decode(x, bauds[i], thrs[i])
+        assert (int(one.status[i]), int(one.clock[i]), int(one.nbits[i]), one.payload(i)) == \
+               (o["status"], o["clock"], o["nbits"], o["data"]), i
+    # pinned host memory, the automatic choice: a batch of 64 MB and more is pipelined
+    big = [np.zeros(5_000_000, np.int16) for _ in range(8)]
+    big[3][1000:1000 + len(caps[0])] = caps[0]
+    bs, bo = A.modem._concat(big)
+    auto = rx.decode_batch(bs, bo, baud_rate=[bauds[0]] * 8, amp_end_threshold=[thrs[0]] * 8)
+    assert isinstance(rx._cache[1], A.modem.PipelinedRxSession)
+    ref = rx.decode_batch(bs, bo, baud_rate=[bauds[0]] * 8, amp_end_threshold=[thrs[0]] * 8, pipeline=1)
+    assert np.array_equal(auto.results, ref.results) and auto.payloads() == ref.payloads()
+    rx.close()
+
+
 def test_ranges_plan_equals_adjacent_plan():
     """afsk_rx_plan_create_ranges over non-adjacent, overlapping and out-of-order ranges of one buffer."""
     rng = np.random.default_rng(21)

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -135,6 +136,10 @@ int afsk_wav_load(const char *const *paths, int n, int threads, const int64_t *h
 {
     if (n < 0 || (n > 0 && (!paths || !h_data_pos || !h_nsamples || !h_offsets || !h_dst || !h_status))) return AFSK_E_ARG;
     if (n == 0) return AFSK_OK;
+    // automatic thread count: leave two cores to the copy-issuing thread and the driver when the H2D is
+    // overlapped (measured on a 16-core host, 1.23 GB from /dev/shm: 12 readers 31.2 ms, 16 readers 32.4 ms,
+    // 24 readers 36.6 ms; without the overlapped copy 16 readers fill the buffer in 22.2 ms)
+    if (threads <= 0 && d_dst) threads = std::max(1, (int)std::thread::hardware_concurrency() - 2);
     threads = clamp_threads(threads, n);
     if (span_samples <= 0) span_samples = (int64_t)32 << 20;            // 64 MB per H2D copy
     // spans of consecutive files, each copied to the device as soon as its last file is in memory
@@ -175,7 +180,8 @@ int afsk_wav_load(const char *const *paths, int n, int threads, const int64_t *h
         AfskDeviceGuard guard(device);
         if (!guard.ok) rc = AFSK_E_CUDA;
         for (int s = 0; s < nspans && rc == AFSK_OK; s++) {
-            while (remaining[s].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+            while (remaining[s].load(std::memory_order_acquire) > 0)
+                std::this_thread::sleep_for(std::chrono::microseconds(20));   // the readers need the cores
             const int64_t a = h_offsets[span_first[s]], b = h_offsets[span_first[s + 1]];
             if (b > a && cudaMemcpyAsync(d_dst + a, h_dst + a, (size_t)(b - a) * 2, cudaMemcpyHostToDevice,
                                          (cudaStream_t)stream) != cudaSuccess) {

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import wave
+import weakref
 from datetime import datetime
 
 import numpy as np
@@ -307,22 +308,29 @@ class PipelinedRxSession:
         self.blob_lo = np.cumsum([0] + [int(sess.out_off[-1]) for sess in self.sessions])
         self.out_off = np.concatenate([sess.out_off[:-1] + self.blob_lo[j] for j, sess in enumerate(self.sessions)] +
                                       [self.blob_lo[-1:]]).astype(np.int64)
-        # two pinned host result sets, used alternately: the D2H copies are truly asynchronous (range j's
-        # results travel while range j+1 is still uploading — the link is full duplex) and the batch a call
-        # returns stays valid until the call after the next one
-        self._host = [(_cabi.PinnedArray((self.B,), _cabi.RX_RESULT_DTYPE),
-                       _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8)) for _ in range(2)]
-        self._flip = 0
+        # pinned host result sets: the D2H copies are truly asynchronous (range j's results travel while
+        # range j+1 is still uploading — the link is full duplex).  A set is re-used only once the RxBatch
+        # it was handed out in is gone (weak reference), so a caller that keeps batches never sees them change.
+        self._host = []                    # [(PinnedArray results, PinnedArray blob), weakref to the last RxBatch | None]
         _cabi.stream_sync(device)          # plan set-up (default stream) is complete before the side streams run
 
+    def _host_set(self):
+        for entry in self._host:
+            if entry[1] is None or entry[1]() is None:
+                return entry
+        entry = [(_cabi.PinnedArray((self.B,), _cabi.RX_RESULT_DTYPE),
+                  _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8)), None]
+        if len(self._host) < 4:            # beyond that the set simply belongs to the batch that holds it
+            self._host.append(entry)
+        return entry
+
     def decode(self, samples: np.ndarray) -> RxBatch:
-        """The returned batch views pinned memory owned by this session: it is overwritten by the second
-        decode after this one (copy what must live longer)."""
+        """The returned batch views pinned host memory that stays untouched for as long as the batch lives."""
         samples = np.ascontiguousarray(samples, dtype=np.int16)
         assert len(samples) >= self.total_samples
-        owner = self._host[self._flip]
+        entry = self._host_set()
+        owner = entry[0]
         res, blob = (h.array for h in owner)
-        self._flip ^= 1
         for j, ((lo, hi), sess) in enumerate(zip(self.ranges, self.sessions)):
             a, b = int(self.offsets[lo]), int(self.offsets[hi])
             if b > a:
@@ -334,6 +342,7 @@ class PipelinedRxSession:
         _cabi.stream_sync(self.device, self.compute_stream)
         out = RxBatch(res, blob[:int(self.blob_lo[-1])], self.out_off)
         out._owner = owner                 # the pinned memory lives as long as a batch refers to it
+        entry[1] = weakref.ref(out)
         return out
 
     def close(self):
@@ -348,7 +357,7 @@ class PipelinedRxSession:
             if st:
                 _cabi.stream_destroy(self.device, st)
                 setattr(self, name, None)
-        self._host = []                    # freed when the last RxBatch viewing them is gone
+        self._host = []                    # the pinned sets are freed when the last RxBatch viewing them is gone
 
     __del__ = close
 
@@ -484,9 +493,7 @@ class Receiver:
         """Decode B captures.  ``samples``: list of int16 arrays, or one concatenated int16 array
         with ``offsets`` (B+1, in samples).  ``baud_rate`` / ``amp_end_threshold`` (arrays of B) override
         this receiver's settings per capture for mixed corpora.  ``pipeline``: number of capture ranges
-        whose upload and decode are overlapped (None: 8 for batches of 64 MB and more, else 1); a
-        pipelined call returns views of session-owned pinned memory that the second call after it
-        overwrites.
+        whose upload and decode are overlapped (None: 8 for batches of 64 MB and more, else 1).
         Raises the reference's exceptions only through ``to_python``; statuses < 0 mark captures on
         which ``load`` would raise."""
         if offsets is None:
@@ -519,14 +526,17 @@ class Receiver:
             lg.warn("Failed to recover clock from received signal.")               # :324
             lg.warn("No data.")                                                    # :423
             return b""
-        lg.debug("Recovered clock. (frame " + str(int(batch.clock[i])) + ")")       # :338
-        lg.debug("Training sequence terminated on frame " + str(int(batch.train_end[i])))   # :368
-        lg.debug("Decoded " + str(int(batch.nbits[i])) + " bits. (including ECC)")  # :380
+        debug = log and _log_level() <= 0        # the stage lines are built only when they would be printed
+        if debug:
+            lg.debug("Recovered clock. (frame " + str(int(batch.clock[i])) + ")")       # :338
+            lg.debug("Training sequence terminated on frame " + str(int(batch.train_end[i])))   # :368
+            lg.debug("Decoded " + str(int(batch.nbits[i])) + " bits. (including ECC)")  # :380
         if st == _cabi.ST_NO_DATA:
             lg.warn("No data.")
             return b""
         data = batch.payload(i)
-        lg.debug("Decoded " + str(len(data)) + " bytes.")                          # :427
+        if debug:
+            lg.debug("Decoded " + str(len(data)) + " bytes.")                          # :427
         if string:
             return data.decode("utf-8")                                            # :428-429
         return data

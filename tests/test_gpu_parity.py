@@ -325,7 +325,18 @@ def test_pipelined_decode_equals_single_plan():
     assert isinstance(rx._cache[1], A.modem.PipelinedRxSession)
     ref = rx.decode_batch(bs, bo, baud_rate=[bauds[0]] * 8, amp_end_threshold=[thrs[0]] * 8, pipeline=1)
     assert np.array_equal(auto.results, ref.results) and auto.payloads() == ref.payloads()
+    # batches a caller keeps are never overwritten by later calls on the same receiver
+    big[5][2000:2000 + len(caps[1])] = caps[1]
+    bs2, _ = A.modem._concat(big)
+    kw = {"baud_rate": [bauds[0]] * 8, "amp_end_threshold": [thrs[0]] * 8}
+    kept = [rx.decode_batch(bs if i % 2 == 0 else bs2, bo, **kw) for i in range(6)]
+    assert isinstance(rx._cache[1], A.modem.PipelinedRxSession)
+    for i, b in enumerate(kept):
+        want = kept[i % 2]
+        assert np.array_equal(b.results, want.results) and b.payloads() == want.payloads(), i
+    assert not np.array_equal(kept[0].results, kept[1].results)
     rx.close()
+    assert kept[0].payload(3) == auto.payload(3)                    # still readable after the receiver is closed
 
 
 def test_ranges_plan_equals_adjacent_plan():

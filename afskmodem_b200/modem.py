@@ -311,15 +311,19 @@ class PipelinedRxSession:
         # pinned host result sets: the D2H copies are truly asynchronous (range j's results travel while
         # range j+1 is still uploading — the link is full duplex).  A set is re-used only once the RxBatch
         # it was handed out in is gone (weak reference), so a caller that keeps batches never sees them change.
-        self._host = []                    # [(PinnedArray results, PinnedArray blob), weakref to the last RxBatch | None]
+        # Two sets exist from the start: a loop that rebinds its result variable alternates between them.
+        self._host = [self._new_host_set() for _ in range(2)]   # [(results, blob) PinnedArrays, weakref to the last RxBatch | None]
         _cabi.stream_sync(device)          # plan set-up (default stream) is complete before the side streams run
+
+    def _new_host_set(self):
+        return [(_cabi.PinnedArray((self.B,), _cabi.RX_RESULT_DTYPE),
+                 _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8)), None]
 
     def _host_set(self):
         for entry in self._host:
             if entry[1] is None or entry[1]() is None:
                 return entry
-        entry = [(_cabi.PinnedArray((self.B,), _cabi.RX_RESULT_DTYPE),
-                  _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8)), None]
+        entry = self._new_host_set()
         if len(self._host) < 4:            # beyond that the set simply belongs to the batch that holds it
             self._host.append(entry)
         return entry

@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     const uint32_t *Pe = P + e;
     const int qL = q * kClockChain;
     const int nitems = ((span + qL - 1) / qL) * q;
-    constexpr int kPmax = AFSK_SYNC_FRAMES + 7;                // last prefix entry a valid candidate can touch
     auto D_at = [&](int i) -> uint32_t {
         return c0 + Pe[i] + Pe[i + 8 * q] - 2u * (Pe[i + q] - Pe[i + 2 * q] + Pe[i + 3 * q] - Pe[i + 4 * q] + Pe[i + 6 * q]);
     };
@@ -706,189 +705,10 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     }
 }
 
-// ------------------------------------------------------------------------ k_demod_small ----
-// Short windows (bf = 8, 16, 24: 6000 / 3000 / 2000 baud): one thread decodes kWpt consecutive
-// windows of kM vectors each, so the per-tile bookkeeping is paid once per 48-64 samples instead of
-// once per 8-24.  Every vector is re-aligned to the window grid with 4 PRMTs (slots >= e from
-// vector i, slots < e from vector i+1); the weights are uniform over the tile (alignment e is per
-// tile) and live in registers; threads visit their windows in a lane-rotated order so that the
-// 128-bit shared-memory loads of a warp fall in different banks.  The window body is branch-free
-// and carries ONE packed accumulator, D = (mark - space) / 2 as in k_demod's merge mode: the byte
-// offsets and plane-bit masks of a thread's windows are per-thread constants, windows whose
-// correlations tie (noise only) are collected in a mask and re-decided from the full sums after the
-// loop, and windows past the end of the capture are masked once per tile.
-template <int kM>
-__device__ __forceinline__ bool small_tie_decide(const uint4 *dp, const uint4 *wt, uint32_t k512)
-{
-    // full mark / space sums of one window (the decision of k_demod's plain mode)
-    constexpr int kBf = 8 * kM;
-    const uint4 sel = wt[kM];
-    int accM = 0, accS = 0, accA = 0;
-    uint4 cur = dp[0];
-#pragma unroll
-    for (int i = 0; i < kM; i++) {
-        const uint4 nxt = dp[i + 1];
-        const uint4 W = wt[i];
-        const uint32_t x0 = prmt(cur.x, nxt.x, sel.x), x1 = prmt(cur.y, nxt.y, sel.y);
-        const uint32_t x2 = prmt(cur.z, nxt.z, sel.z), x3 = prmt(cur.w, nxt.w, sel.w);
-        accum4_full(x0, x1, W.x, W.z, k512, accM, accS, accA);
-        accum4_full(x2, x3, W.y, W.w, k512, accM, accS, accA);
-        cur = nxt;
-    }
-    // acc = 256 * T.n + T.c with |T.c| <= 24
-    const int Um = (int)((unsigned)accM << 24) >> 24, Us = (int)((unsigned)accS << 24) >> 24;
-    const int du = Um - Us;
-    bool b1 = du > 0;
-    if (du == 0) {
-        const int Nm = (accM - Um) >> 8, Ns = (accS - Us) >> 8;
-        if (Ns > Nm) {
-            const int M2 = 65535 * kBf - 65534 * Um + 2 * Nm;
-            const int S2 = M2 + 2 * (Ns - Nm);
-            b1 = (S2 - M2 >= 2 * kBf) || (M2 < (S2 / (2 * kBf)) * (2 * kBf));   // floor(M/bf) < floor(S/bf)
-        }
-    }
-    return b1;
-}
-
-template <int kM, int kWpt>
-__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_small(const DemodParams p)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int S = p.stages;
-    uint8_t *stage_base = smem;
-    // per alignment e: [0, kM) mark / space weights, [kM] PRMT selectors, [kM + 1, 2 kM + 1) D weights
-    constexpr int kEnt = 2 * kM + 1;
-    uint4 *wtab = reinterpret_cast<uint4 *>(smem + (size_t)S * p.stage_bytes);     // [8 alignments][kEnt]
-    TileMeta *meta = reinterpret_cast<TileMeta *>(wtab + 8 * kEnt);
-    uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
-    uint64_t *empty = full + kMaxStages;
-    constexpr int kBf = 8 * kM, kSeg = kBf * kWpt, kLanesPerWord = 32 / kWpt;
-
-    // weights of re-aligned vector i at alignment e: slot s holds window sample 8i + ((s - e) mod 8)
-    if (tid < 8 * kEnt) {
-        const int e = tid / kEnt, i = tid % kEnt;
-        if (i == kM) {
-            uint32_t sel[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) sel[j] = (2 * j >= e) ? 0x3210u : ((2 * j + 1 < e) ? 0x7654u : 0x3254u);
-            wtab[tid] = make_uint4(sel[0], sel[1], sel[2], sel[3]);
-        } else {
-            const int iv = i < kM ? i : i - kM - 1;
-            const int q = kBf >> 2;
-            uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u};
-#pragma unroll
-            for (int sl = 0; sl < 8; sl++) {
-                const int r = 8 * iv + ((sl - e + 8) & 7), qd = r / q, sh = 8 * (sl & 3);
-                mk[sl >> 2] |= ((qd & 1) ? 0xFFu : 0x01u) << sh;
-                sp[sl >> 2] |= ((qd & 2) ? 0xFFu : 0x01u) << sh;
-            }
-            if (i < kM) {
-                wtab[tid] = make_uint4(mk[0], mk[1], sp[0], sp[1]);
-            } else {
-                // D = (mark - space) / 2: the mark weight where the two differ (0x01 ^ 0xFF = 0xFE), else 0
-                const uint32_t x0 = mk[0] ^ sp[0], x1 = mk[1] ^ sp[1];
-                wtab[tid] = make_uint4(mk[0] & prmt(x0, x0, 0xBA98u), mk[1] & prmt(x1, x1, 0xBA98u), 0u, 0u);
-            }
-        }
-    }
-    if (tid == 0) {
-        for (int s = 0; s < S; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerThreads / 32);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
-    if (ntile <= 0) return;
-    if (warp == kConsumerThreads / 32) {
-        demod_produce(p, ntile, stage_base, meta, full, empty);
-        return;
-    }
-
-    const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
-    // the thread's j-th visit is to its window (j + tid) mod kWpt: byte offset in the tile and plane bit
-    uint32_t woff[kWpt], wbit[kWpt];
-#pragma unroll
-    for (int j = 0; j < kWpt; j++) {
-        const int jj = (j + tid) & (kWpt - 1);
-        woff[j] = (uint32_t)(tid * kSeg + jj * kBf) * 2u;
-        wbit[j] = 1u << jj;
-    }
-    int s = 0;
-    uint32_t ph = 0;
-    for (int n = 0; n < ntile; ++n) {
-        mbar_wait(&full[s], ph);
-        const TileMeta m = meta[s];
-        uint32_t bits = 0, quiet = 0;
-        if (m.nwin > 0) {
-            const uint4 *wt = wtab + (m.e0 & 7) * kEnt;
-            uint2 Dw[kM];
-#pragma unroll
-            for (int i = 0; i < kM; i++) Dw[i] = *reinterpret_cast<const uint2 *>(wt + kM + 1 + i);
-            const uint4 sel = wt[kM];
-            // kSeg % 8 == 0: the thread's first vector is e0 / 8 + tid * kSeg / 8
-            const uint8_t *tb = stage_base + (size_t)s * p.stage_bytes + (m.e0 >> 3) * 16;
-            uint32_t ties = 0;
-#pragma unroll
-            for (int j = 0; j < kWpt; j++) {
-                const uint4 *dp = reinterpret_cast<const uint4 *>(tb + woff[j]);
-                int accD = 0, accA = 0;
-                uint4 cur = dp[0];
-#pragma unroll
-                for (int i = 0; i < kM; i++) {
-                    const uint4 nxt = dp[i + 1];
-                    const uint32_t x0 = prmt(cur.x, nxt.x, sel.x), x1 = prmt(cur.y, nxt.y, sel.y);
-                    const uint32_t x2 = prmt(cur.z, nxt.z, sel.z), x3 = prmt(cur.w, nxt.w, sel.w);
-                    accum4_d(x0, x1, Dw[i].x, k512, accD, accA);
-                    accum4_d(x2, x3, Dw[i].y, k512, accD, accA);
-                    cur = nxt;
-                }
-                // accD = 256 * D.n + D.c with |D.c| <= 12: D.c = (Um - Us) / 2 decides; when it is zero the
-                // window is a 0 unless Ns > Nm (D.n < 0), and only then are the two floors compared
-                const int dl = (int)((unsigned)accD << 24);
-                if (dl > 0) bits |= wbit[j];
-                if (dl == 0 && accD < 0) ties |= wbit[j];
-                if (accA < m.thr_bf) quiet |= wbit[j];
-            }
-            if (ties) {
-                for (int jj = 0; jj < kWpt; jj++)
-                    if ((ties >> jj) & 1u) {
-                        const uint4 *dp = reinterpret_cast<const uint4 *>(tb + (uint32_t)(tid * kSeg + jj * kBf) * 2u);
-                        if (small_tie_decide<kM>(dp, wt, k512)) bits |= 1u << jj;
-                    }
-            }
-            // windows past the capture's last one
-            const int nvalid = m.nwin - tid * kWpt;
-            const uint32_t vm = nvalid >= kWpt ? 0xFFFFFFFFu : (nvalid <= 0 ? 0u : (1u << nvalid) - 1u);
-            bits &= vm;
-            quiet &= vm;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (m.nwin > 0) {
-            // kLanesPerWord threads hold the kWpt-bit pieces of one plane word
-            uint32_t bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
-            uint32_t qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
-#pragma unroll
-            for (int o = 1; o < kLanesPerWord; o <<= 1) {
-                bw |= __shfl_xor_sync(0xFFFFFFFFu, bw, o);
-                qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
-            }
-            const int word = (tid * kWpt) >> 5;
-            if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin) p.planes[m.word_base + word] = make_uint2(bw, qw);
-        }
-        if (++s == S) { s = 0; ph ^= 1u; }
-    }
-}
-
 // ------------------------------------------------------------------------ k_demod_shift ----
 // Short windows that are a multiple of 4 but not of 8 samples (bf = 12, 20: 4000 / 2400 baud).  One
 // thread decodes kWpt consecutive windows (kBf * kWpt samples, a multiple of 8).  A window boundary
-// then falls in the middle of a 16-byte vector, so the rotate-in-place trick of k_demod_small does
-// not apply; instead the tile's alignment e (0..7, uniform over the tile) selects one of eight
+// then falls in the middle of a 16-byte vector; here the tile's alignment e (0..7, uniform over the tile) selects one of eight
 // fully unrolled bodies in which the thread's words are picked at compile-time positions (even e:
 // plain register renaming; odd e: one PRMT per word to splice the two half-words).  Every group of
 // 4 samples lies inside one window (kBf % 4 == 0) and its +/-1 template weights are immediates.
@@ -1013,6 +833,176 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodPar
             }
             const int word = (tid * kWpt) >> 5;
             if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin) p.planes[m.word_base + word] = make_uint2(bw, qw);
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+    }
+}
+
+// ------------------------------------------------------------------------- k_demod_lane ----
+// Short windows of whole vectors (bf = 8, 16, 24: 6000 / 3000 / 2000 baud), lane-major: a consumer warp
+// owns kJ * 32 consecutive windows of the tile and lane t decodes windows t, t + 32, ... of them, so the
+// 128-bit loads of a warp are consecutive vectors (no bank conflicts, no rotation) and the 32 decisions of
+// one step ARE a plane word (warp ballot).  The tile's alignment e (0..7, uniform over the tile because
+// bf % 8 == 0) selects one of eight fully unrolled bodies: the window's words are picked at compile-time
+// positions (even e: register renaming, odd e: one PRMT per word), the template weights are immediates,
+// and the groups of 4 samples that lie in the first or last quarter of the bit — where mark and space
+// agree, D = (mark - space) / 2 = 0 — are only summed for the end detector (3 instead of 11 instructions).
+__host__ __device__ constexpr uint32_t d_weights4(int bf, int pos)
+{
+    // signed bytes of D = (mark - space) / 2 for window samples pos .. pos+3: 0, -1, +1, 0 per quarter
+    uint32_t w = 0;
+    for (int s = 0; s < 4; s++) {
+        const int qd = (pos + s) / (bf / 4);
+        w |= (qd == 1 ? 0xFFu : (qd == 2 ? 0x01u : 0x00u)) << (8 * s);
+    }
+    return w;
+}
+
+// the words of one window (samples 2i, 2i + 1 in X[i]) out of the vectors at v, for tile alignment kE
+template <int kM, int kE>
+__device__ __forceinline__ void lane_window_words(const uint4 *v, uint32_t (&X)[4 * kM])
+{
+    uint32_t W[4 * (kM + 1)];
+#pragma unroll
+    for (int i = 0; i <= kM; i++) {
+        if (i < kM || kE > 0) {                      // an aligned tile never touches the extra vector
+            const uint4 q = v[i];
+            W[4 * i] = q.x; W[4 * i + 1] = q.y; W[4 * i + 2] = q.z; W[4 * i + 3] = q.w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * kM; i++) {
+        if ((kE & 1) == 0) X[i] = W[i + kE / 2];
+        else X[i] = prmt(W[i + (kE - 1) / 2], W[i + (kE + 1) / 2], 0x5432u);
+    }
+}
+
+template <int kM, int kJ, int kE>
+__device__ __forceinline__ void lane_decode(const uint4 *dp, uint32_t k512, int thr_bf, uint32_t (&bw)[kJ], uint32_t (&qw)[kJ])
+{
+    constexpr int kBf = 8 * kM;
+    const int lane = threadIdx.x & 31;
+    uint32_t tb[kJ];
+#pragma unroll
+    for (int j = 0; j < kJ; j++) {
+        uint32_t X[4 * kM];
+        lane_window_words<kM, kE>(dp + j * 32 * kM, X);
+        int accD = 0, accA = 0;
+#pragma unroll
+        for (int g = 0; g < 2 * kM; g++) {
+            const uint32_t dw = d_weights4(kBf, 4 * g);
+            if (dw != 0u) accum4_d(X[2 * g], X[2 * g + 1], dw, k512, accD, accA);
+            else accum4_a(X[2 * g], X[2 * g + 1], accA);
+        }
+        // accD = 256 * D.n + D.c, |D.c| <= bf / 2: D.c = (Um - Us) / 2 decides; when it is zero the window
+        // is a 0 unless Ns > Nm (D.n < 0), and only then are the two floors compared (below)
+        const int dl = (int)((unsigned)accD << 24);
+        bw[j] = __ballot_sync(0xFFFFFFFFu, dl > 0);
+        qw[j] = __ballot_sync(0xFFFFFFFFu, accA < thr_bf);
+        tb[j] = __ballot_sync(0xFFFFFFFFu, dl == 0 && accD < 0);
+    }
+    // tied correlations (noise-only windows): the full mark / space sums decide, as in k_demod's plain mode
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < kJ; j++) any |= tb[j];
+    if (any) {
+#pragma unroll 1
+        for (int j = 0; j < kJ; j++) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int jj = 0; jj < kJ; jj++) t = (jj == j) ? tb[jj] : t;
+            if (t == 0) continue;
+            bool b1 = false;
+            if ((t >> lane) & 1u) {
+                uint32_t X[4 * kM];
+                lane_window_words<kM, kE>(dp + j * 32 * kM, X);
+                int accM = 0, accS = 0, accA = 0;
+#pragma unroll
+                for (int g = 0; g < 2 * kM; g++)
+                    accum4_full(X[2 * g], X[2 * g + 1], tone_weights4(kBf, 4 * g, false), tone_weights4(kBf, 4 * g, true), k512,
+                                accM, accS, accA);
+                const int Um = (int)((unsigned)accM << 24) >> 24, Us = (int)((unsigned)accS << 24) >> 24;
+                const int Nm = (accM - Um) >> 8, Ns = (accS - Us) >> 8;
+                if (Um == Us && Ns > Nm) {
+                    const int M2 = 65535 * kBf - 65534 * Um + 2 * Nm;
+                    const int S2 = M2 + 2 * (Ns - Nm);
+                    b1 = (S2 - M2 >= 2 * kBf) || (M2 < (S2 / (2 * kBf)) * (2 * kBf));   // floor(M/bf) < floor(S/bf)
+                } else {
+                    b1 = Um > Us;
+                }
+            }
+            const uint32_t fix = __ballot_sync(0xFFFFFFFFu, b1);
+#pragma unroll
+            for (int jj = 0; jj < kJ; jj++) bw[jj] |= (jj == j) ? fix : 0u;
+        }
+    }
+}
+
+template <int kM, int kJ>
+__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_lane(const DemodParams p)
+{
+    static_assert(kJ * 32 * (kConsumerThreads / 32) * 8 * kM * 2 <= 64 * 1024, "tile");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.stages;
+    uint8_t *stage_base = smem;
+    TileMeta *meta = reinterpret_cast<TileMeta *>(smem + (size_t)S * p.stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
+    uint64_t *empty = full + kMaxStages;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
+    if (ntile <= 0) return;
+    if (warp == kConsumerThreads / 32) {
+        demod_produce(p, ntile, stage_base, meta, full, empty);
+        return;
+    }
+
+    const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
+    const int win0 = warp * kJ * 32;                  // first window of this warp in the tile
+    int s = 0;
+    uint32_t ph = 0;
+    for (int n = 0; n < ntile; ++n) {
+        mbar_wait(&full[s], ph);
+        const TileMeta m = meta[s];
+        uint32_t bw[kJ], qw[kJ];
+#pragma unroll
+        for (int j = 0; j < kJ; j++) { bw[j] = 0u; qw[j] = 0u; }
+        const bool work = m.nwin > win0;              // warp-uniform: the warp has at least one valid window
+        if (work) {
+            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) +
+                              (win0 + lane) * kM;
+            switch (m.e0 & 7) {                       // uniform over the CTA
+            case 0: lane_decode<kM, kJ, 0>(dp, k512, m.thr_bf, bw, qw); break;
+            case 1: lane_decode<kM, kJ, 1>(dp, k512, m.thr_bf, bw, qw); break;
+            case 2: lane_decode<kM, kJ, 2>(dp, k512, m.thr_bf, bw, qw); break;
+            case 3: lane_decode<kM, kJ, 3>(dp, k512, m.thr_bf, bw, qw); break;
+            case 4: lane_decode<kM, kJ, 4>(dp, k512, m.thr_bf, bw, qw); break;
+            case 5: lane_decode<kM, kJ, 5>(dp, k512, m.thr_bf, bw, qw); break;
+            case 6: lane_decode<kM, kJ, 6>(dp, k512, m.thr_bf, bw, qw); break;
+            default: lane_decode<kM, kJ, 7>(dp, k512, m.thr_bf, bw, qw); break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (work && lane < kJ) {
+            // lane j stores plane word j of the warp, windows past the capture's last one masked off
+            uint32_t b = 0u, q = 0u;
+#pragma unroll
+            for (int j = 0; j < kJ; j++) { b = (lane == j) ? bw[j] : b; q = (lane == j) ? qw[j] : q; }
+            const int nv = m.nwin - (win0 + 32 * lane);
+            if (nv > 0) {
+                const uint32_t vm = nv >= 32 ? 0xFFFFFFFFu : (1u << nv) - 1u;
+                p.planes[m.word_base + (win0 >> 5) + lane] = make_uint2(b & vm, q & vm);
+            }
         }
         if (++s == S) { s = 0; ph ^= 1u; }
     }
@@ -1396,7 +1386,7 @@ __global__ void __launch_bounds__(32) k_gate_multi(const int32_t *__restrict__ a
 
 struct Group {
     int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, stage_bytes = 0, stages = 0;
-    int small_wpt = 0;            // > 0: k_demod_small<bf/8, small_wpt>
+    int small_wpt = 0;            // > 0: k_demod_lane<bf/8, small_wpt>
     int shift_wpt = 0;            // > 0: k_demod_shift<bf, shift_wpt>
     size_t smem = 0;
     int grid = 0;
@@ -1413,11 +1403,11 @@ struct Group {
 
 static cudaError_t demod_set_smem_attr()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_demod_small<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_demod_lane<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_small<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 #define X(NT, MG) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod<NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     AFSK_DEMOD_VARIANTS(X)
@@ -1463,11 +1453,8 @@ constexpr size_t kDemodMaxStages = 3;
 
 static size_t demod_smem_bytes(const Group &g)
 {
-    if (g.shift_wpt)
+    if (g.shift_wpt || g.small_wpt)
         return (size_t)g.stages * g.stage_bytes + kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t);
-    if (g.small_wpt)
-        return (size_t)g.stages * g.stage_bytes + (size_t)8 * (2 * (g.bf / 8) + 1) * 16 + kMaxStages * sizeof(TileMeta) +
-               2 * kMaxStages * sizeof(uint64_t);
     return (size_t)g.stages * g.stage_bytes + (size_t)(1 << g.tpw_log2) * (8 * (2 * g.nt + 1) + 1) * 16 +
            kMaxStages * sizeof(TileMeta) + 2 * kMaxStages * sizeof(uint64_t) + 2 * kConsumerThreads;
 }
@@ -1486,7 +1473,8 @@ static bool configure_group(Group &g, int bf)
     g.bf = bf;
     g.tpw_log2 = 0;
     if (bf == 8 || bf == 16 || bf == 24) {
-        // short windows: several windows per thread (k_demod_small)
+        // short windows: lane-major tiles of 256 * kJ windows (k_demod_lane<bf/8, kJ>), kJ = 8 / 4 / 2.  Smaller
+        // tiles are slower (6000 baud, same box: 32 KB tiles 6661 GB/s, 16 KB 5756-6079, 8 KB 4715)
         g.small_wpt = bf == 8 ? 8 : (bf == 16 ? 4 : 2);
         g.seg = bf * g.small_wpt;
         g.nv = g.seg / 8 + 1;
@@ -1512,7 +1500,7 @@ static bool configure_group(Group &g, int bf)
     // Segments of at most 48 samples per thread.  The thread stride in shared memory is 2 * seg bytes:
     // 40 samples (80 B) is conflict-free for 128-bit loads and 48 is 2-way, both reach the HBM ceiling;
     // 32 is 4-way (75-89 % of it: 1500 / 750 / 375 baud).  Measured and rejected: segments of 64
-    // samples in merge mode (8-way, 57 %) and two 32-sample windows per thread (k_demod_small<4,2>, 83 %).
+    // samples in merge mode (8-way, 57 %) and two 32-sample windows per thread (83 %).
     while ((bf >> g.tpw_log2) > 48 && g.tpw_log2 < 3) g.tpw_log2++;
     const int tpw = 1 << g.tpw_log2;
     g.seg = (bf + tpw - 1) / tpw;
@@ -1774,16 +1762,16 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.nt = g.nt; p.merge = g.merge; p.wt = g.wt;
         p.stage_bytes = g.stage_bytes; p.stages = g.stages;
         // L2 evict-first on the bulk copies (the samples are read once).  Same-box A/B: k_demod +2-6 %
-        // (c2 0.768 -> 0.745 ms, 600 baud 0.819 -> 0.770), k_demod_shift +1-2.5 %, k_demod_small 0 to -10 %
+        // (c2 0.768 -> 0.745 ms, 600 baud 0.819 -> 0.770), k_demod_shift +1-2.5 %, the short-window kernel 0 to -10 %
         // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 forces.
         const int l2_force = getenv("AFSK_L2_HINT") ? atoi(getenv("AFSK_L2_HINT")) : -1;
         p.l2_hint = l2_force >= 0 ? l2_force : (g.small_wpt ? 0 : 1);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        if (g.small_wpt && g.bf == 8) k_demod_small<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 16) k_demod_small<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 24) k_demod_small<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);

@@ -888,11 +888,18 @@ __device__ __forceinline__ void lane_decode(const uint4 *dp, uint32_t k512, int 
         uint32_t X[4 * kM];
         lane_window_words<kM, kE>(dp + j * 32 * kM, X);
         int accD = 0, accA = 0;
+        // D = 0 outside samples [q, 3q) = words [q/2, 3q/2): those q words are classified in adjacent pairs,
+        // the other q words (the first and last q/2) are paired among themselves for the amplitude only
+        constexpr int kQ = kBf / 4, kH = kQ / 2;
 #pragma unroll
-        for (int g = 0; g < 2 * kM; g++) {
-            const uint32_t dw = d_weights4(kBf, 4 * g);
-            if (dw != 0u) accum4_d(X[2 * g], X[2 * g + 1], dw, k512, accD, accA);
-            else accum4_a(X[2 * g], X[2 * g + 1], accA);
+        for (int k = 0; k < kH; k++)
+            accum4_d(X[kH + 2 * k], X[kH + 2 * k + 1], d_weights4(kBf, kQ + 4 * k), k512, accD, accA);
+#pragma unroll
+        for (int k = 0; k < kH; k++) {
+            // k-th pair of the list 0 .. q/2-1, 3q/2 .. 2q-1
+            constexpr int kFirstHi = 3 * kH;
+            const int a = 2 * k, b = 2 * k + 1;
+            accum4_a(X[a < kH ? a : kFirstHi + (a - kH)], X[b < kH ? b : kFirstHi + (b - kH)], accA);
         }
         // accD = 256 * D.n + D.c, |D.c| <= bf / 2: D.c = (Um - Us) / 2 decides; when it is zero the window
         // is a 0 unless Ns > Nm (D.n < 0), and only then are the two floors compared (below)
@@ -938,10 +945,10 @@ __device__ __forceinline__ void lane_decode(const uint4 *dp, uint32_t k512, int 
     }
 }
 
-template <int kM, int kJ>
-__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_lane(const DemodParams p)
+template <int kM, int kJ, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32 + 32, 2) k_demod_lane(const DemodParams p)
 {
-    static_assert(kJ * 32 * (kConsumerThreads / 32) * 8 * kM * 2 <= 64 * 1024, "tile");
+    static_assert(kJ * 32 * kWarps * 8 * kM * 2 <= 64 * 1024, "tile");
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.stages;
@@ -953,7 +960,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_lane(const DemodPara
     if (tid == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerThreads / 32);
+            mbar_init(&empty[s], kWarps);
         }
         mbar_fence_init();
     }
@@ -961,7 +968,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_lane(const DemodPara
 
     const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
     if (ntile <= 0) return;
-    if (warp == kConsumerThreads / 32) {
+    if (warp == kWarps) {
         demod_produce(p, ntile, stage_base, meta, full, empty);
         return;
     }
@@ -1403,11 +1410,11 @@ struct Group {
 
 static cudaError_t demod_set_smem_attr()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_demod_lane<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_demod_lane<1, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<2, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<3, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 #define X(NT, MG) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod<NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     AFSK_DEMOD_VARIANTS(X)
@@ -1473,7 +1480,7 @@ static bool configure_group(Group &g, int bf)
     g.bf = bf;
     g.tpw_log2 = 0;
     if (bf == 8 || bf == 16 || bf == 24) {
-        // short windows: lane-major tiles of 256 * kJ windows (k_demod_lane<bf/8, kJ>), kJ = 8 / 4 / 2.  Smaller
+        // short windows: lane-major tiles of 256 * kJ windows (k_demod_lane<bf/8, kJ, 8 warps>), kJ = 8 / 4 / 2.  Smaller
         // tiles are slower (6000 baud, same box: 32 KB tiles 6661 GB/s, 16 KB 5756-6079, 8 KB 4715)
         g.small_wpt = bf == 8 ? 8 : (bf == 16 ? 4 : 2);
         g.seg = bf * g.small_wpt;
@@ -1769,9 +1776,9 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
         else launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out/r1g
+export AB_ROUNDS=4
+timeout 400 python tools/ab_demod.py c3 "AFSK_L2_HINT=0" "AFSK_L2_HINT=2" "AFSK_L2_HINT=4" "AFSK_L2_HINT=6" "AFSK_L2_HINT=7" 2>&1 | tee gpurun_out/r1g/ab5_c3.txt

@@ -1,7 +1,7 @@
 #!/bin/bash
-# round-1e/f evidence capture (run under gpurun, one GPU): new k_demod_small / k_clock / k_frame_warp
+# evidence capture of the final code of a round (run under gpurun, one GPU): new k_demod_small / k_clock / k_frame_warp
 set -x
-O=gpurun_out/r1h; mkdir -p $O
+O=gpurun_out/final; mkdir -p $O
 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_c2_reference.json 2>$O/ref.err
 python bench.py > $O/bench_c2_n1.json 2> $O/bench_c2_n1.err
 for w in c3 c4 c5; do python bench.py --workload $w > $O/bench_${w}_n1.json 2> $O/bench_${w}.err; done

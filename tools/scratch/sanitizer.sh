@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/r1e; mkdir -p $O
+O=gpurun_out/final; mkdir -p $O
 python tools/scratch/files_breakdown.py 2>&1 | tee $O/files_breakdown.txt
 K="golden_rx_one_mixed or random_sweep or every_alignment or fuzz or gate or golden_tx or unequal or threshold_edge or empty_and_ragged or ranges_plan"
 for t in memcheck initcheck synccheck; do

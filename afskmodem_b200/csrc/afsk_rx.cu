@@ -845,8 +845,9 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodPar
 // one step ARE a plane word (warp ballot).  The tile's alignment e (0..7, uniform over the tile because
 // bf % 8 == 0) selects one of eight fully unrolled bodies: the window's words are picked at compile-time
 // positions (even e: register renaming, odd e: one PRMT per word), the template weights are immediates,
-// and the groups of 4 samples that lie in the first or last quarter of the bit — where mark and space
-// agree, D = (mark - space) / 2 = 0 — are only summed for the end detector (3 instead of 11 instructions).
+// and the words of the first and last quarter of the bit — where mark and space agree, D = (mark -
+// space) / 2 = 0 — are paired among themselves and only summed for the end detector (3 instead of 11
+// instructions per 4 samples).
 __host__ __device__ constexpr uint32_t d_weights4(int bf, int pos)
 {
     // signed bytes of D = (mark - space) / 2 for window samples pos .. pos+3: 0, -1, +1, 0 per quarter

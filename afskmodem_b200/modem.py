@@ -304,16 +304,23 @@ class PipelinedRxSession:
         self.compute_stream = _cabi.stream_create(device)
         self.launches = sum(sess.launches for sess in self.sessions)
         # one host result set for the whole batch; every range downloads into its slice
-        self.res_lo = np.cumsum([0] + [sess.B for sess in self.sessions])
-        self.blob_lo = np.cumsum([0] + [int(sess.out_off[-1]) for sess in self.sessions])
-        self.out_off = np.concatenate([sess.out_off[:-1] + self.blob_lo[j] for j, sess in enumerate(self.sessions)] +
-                                      [self.blob_lo[-1:]]).astype(np.int64)
+        self.res_lo, self.blob_lo, self.out_off = self.merged_layout([sess.out_off for sess in self.sessions])
         # pinned host result sets: the D2H copies are truly asynchronous (range j's results travel while
         # range j+1 is still uploading — the link is full duplex).  A set is re-used only once the RxBatch
         # it was handed out in is gone (weak reference), so a caller that keeps batches never sees them change.
         # Two sets exist from the start: a loop that rebinds its result variable alternates between them.
         self._host = [self._new_host_set() for _ in range(2)]   # [(results, blob) PinnedArrays, weakref to the last RxBatch | None]
         _cabi.stream_sync(device)          # plan set-up (default stream) is complete before the side streams run
+
+    @staticmethod
+    def merged_layout(sub_out_offs):
+        """Per-range payload offsets (each starting at 0, length B_j + 1) -> (first result index of every
+        range, first blob byte of every range, payload offsets of the whole batch)."""
+        res_lo = np.cumsum([0] + [len(o) - 1 for o in sub_out_offs]).astype(np.int64)
+        blob_lo = np.cumsum([0] + [int(o[-1]) for o in sub_out_offs]).astype(np.int64)
+        out_off = np.concatenate([np.asarray(o[:-1], dtype=np.int64) + blob_lo[j] for j, o in enumerate(sub_out_offs)] +
+                                 [blob_lo[-1:]]).astype(np.int64)
+        return res_lo, blob_lo, out_off
 
     def _new_host_set(self):
         return [(_cabi.PinnedArray((self.B,), _cabi.RX_RESULT_DTYPE),

@@ -114,3 +114,20 @@ def test_product_never_imports_the_oracle():
                     if isinstance(node, (ast.Import, ast.ImportFrom)):
                         names = [a.name for a in node.names] + [getattr(node, "module", "") or ""]
                         assert not any("oracle" in n for n in names), path
+
+
+def test_pipelined_layout_merges_ranges_like_one_plan():
+    """PipelinedRxSession keeps one result set for the whole batch: the per-range payload offsets are
+    shifted into one blob, results are indexed range after range (pure bookkeeping, no device)."""
+    from afskmodem_b200.modem import PipelinedRxSession
+    from afskmodem_b200.shard import shard_captures
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(0, 50_000, 41)
+    caps = (lengths // 40 // 14 + 16 + 15) & ~15                 # per-capture capacities as a plan would lay them out
+    ranges = [(lo, hi) for lo, hi in shard_captures(lengths, 8) if hi > lo]
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(lengths)
+    subs = [np.concatenate([[0], np.cumsum(caps[lo:hi])]) for lo, hi in ranges]
+    res_lo, blob_lo, out_off = PipelinedRxSession.merged_layout(subs)
+    assert list(res_lo) == [lo for lo, _ in ranges] + [len(lengths)]
+    assert np.array_equal(out_off, np.concatenate([[0], np.cumsum(caps)]))
+    assert list(blob_lo) == [int(out_off[lo]) for lo, _ in ranges] + [int(out_off[-1])]

@@ -455,7 +455,10 @@ class WavBatch:
 
 
 class Receiver:
-    """Receiver(baud_rate, amp_start_threshold, amp_end_threshold) — afskmodem.py:274-430."""
+    """Receiver(baud_rate, amp_start_threshold, amp_end_threshold) — afskmodem.py:274-430.
+
+    Unlike the reference's, an instance keeps state between calls (the plan and device buffers of the
+    last batch layout): use one Receiver per thread, or serialise calls on a shared one."""
 
     def __init__(self, baud_rate: int = 1200, amp_start_threshold: int = 18000,
                  amp_end_threshold: int = 14000, device: int = 0):

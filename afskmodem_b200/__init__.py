@@ -11,10 +11,10 @@ All signal processing runs in hand-written CUDA kernels for sm_100a (libafsk_b20
 LOG_LEVEL = 0
 
 from ._cabi import AfskError, LIB_PATH  # noqa: E402
-from .modem import (ECC, Log, Receiver, RxBatch, RxSession, Transmitter, TxBatch, TxSession,  # noqa: E402
-                    Waveforms, WavBatch, read_wav_frames, write_wav_batch, write_wav_frames)
+from .modem import (ECC, Log, PipelinedRxSession, Receiver, RxBatch, RxSession, Transmitter, TxBatch,  # noqa: E402
+                    TxSession, Waveforms, WavBatch, read_wav_frames, write_wav_batch, write_wav_frames)
 from .shard import shard_captures  # noqa: E402
 
-__all__ = ["LOG_LEVEL", "Log", "Waveforms", "ECC", "Receiver", "Transmitter", "RxBatch", "RxSession",
+__all__ = ["LOG_LEVEL", "Log", "Waveforms", "ECC", "Receiver", "Transmitter", "RxBatch", "RxSession", "PipelinedRxSession",
            "TxBatch", "TxSession", "AfskError", "LIB_PATH", "read_wav_frames", "write_wav_frames", "WavBatch", "write_wav_batch",
            "shard_captures"]

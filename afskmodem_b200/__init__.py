@@ -11,10 +11,11 @@ All signal processing runs in hand-written CUDA kernels for sm_100a (libafsk_b20
 LOG_LEVEL = 0
 
 from ._cabi import AfskError, LIB_PATH  # noqa: E402
-from .modem import (ECC, Log, PipelinedRxSession, Receiver, RxBatch, RxSession, Transmitter, TxBatch,  # noqa: E402
-                    TxSession, Waveforms, WavBatch, read_wav_frames, write_wav_batch, write_wav_frames)
-from .shard import shard_captures  # noqa: E402
+from .modem import (ECC, Log, PipelinedRxSession, Receiver, RxBatch, RxSession, ShardedRxSession, SoundInput,  # noqa: E402
+                    SoundOutput, Transmitter, TxBatch, TxSession, Waveforms, WavBatch, read_wav_frames, write_wav_batch,
+                    write_wav_frames)
+from .shard import capture_cost, gather_rx, shard_captures  # noqa: E402
 
-__all__ = ["LOG_LEVEL", "Log", "Waveforms", "ECC", "Receiver", "Transmitter", "RxBatch", "RxSession", "PipelinedRxSession",
+__all__ = ["LOG_LEVEL", "Log", "Waveforms", "ECC", "Receiver", "Transmitter", "RxBatch", "RxSession", "PipelinedRxSession", "ShardedRxSession", "SoundInput", "SoundOutput",
            "TxBatch", "TxSession", "AfskError", "LIB_PATH", "read_wav_frames", "write_wav_frames", "WavBatch", "write_wav_batch",
-           "shard_captures"]
+           "shard_captures", "capture_cost", "gather_rx"]

@@ -17,14 +17,15 @@ LIB_PATH = os.environ.get("AFSK_LIB_PATH") or os.path.join(_HERE, "libafsk_b200.
 AFSK_OK, AFSK_E_ARG, AFSK_E_CUDA, AFSK_E_BAUD, AFSK_E_UNSUPPORTED = 0, -1, -2, -3, -4
 ST_OK, ST_NO_CLOCK, ST_NO_DATA = 0, 1, 2
 ST_EXC_WAVELEN, ST_EXC_INDEX, ST_EXC_BAUD = -1, -2, -3
+OPT_FRAME_KERNEL, OPT_L2_HINT = 1, 2
 
 # every symbol include/afsk_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
     "afsk_abi_version", "afsk_last_error", "afsk_device_count", "afsk_device_info", "afsk_malloc",
     "afsk_free", "afsk_host_alloc", "afsk_host_free", "afsk_memcpy_h2d", "afsk_memcpy_d2h",
     "afsk_memset", "afsk_stream_create", "afsk_stream_destroy", "afsk_stream_sync", "afsk_stream_wait_stream",
-    "afsk_tone_lengths", "afsk_rx_plan_create", "afsk_rx_plan_create_ranges", "afsk_rx_plan_destroy", "afsk_rx_plan_out_offsets",
-    "afsk_rx_plan_launches", "afsk_rx_plan_set_timing", "afsk_rx_plan_demod_time", "afsk_rx_decode", "afsk_rx_plan_planes", "afsk_rx_decode_host",
+    "afsk_tone_lengths", "afsk_rx_plan_create", "afsk_rx_plan_create_ranges", "afsk_rx_plan_reset", "afsk_rx_plan_set_option", "afsk_rx_plan_destroy", "afsk_rx_plan_out_offsets",
+    "afsk_rx_plan_launches", "afsk_rx_plan_set_timing", "afsk_rx_plan_demod_time", "afsk_rx_decode", "afsk_rx_plan_planes", "afsk_rx_decode_host", "afsk_rx_host_release",
     "afsk_rx_out_capacity", "afsk_rx_gate", "afsk_rx_gate_multi", "afsk_tx_num_samples", "afsk_tx_plan_create",
     "afsk_tx_plan_destroy", "afsk_tx_plan_out_offsets", "afsk_tx_synth", "afsk_tx_synth_host",
     "afsk_wav_probe", "afsk_wav_load", "afsk_wav_save",
@@ -78,6 +79,9 @@ def lib():
     L.afsk_tone_lengths.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.afsk_rx_plan_create.argtypes = [C.c_int, C.c_int, i64p, i32p, i32p, C.POINTER(vp)]
     L.afsk_rx_plan_create_ranges.argtypes = [C.c_int, C.c_int, i64p, i64p, i32p, i32p, C.POINTER(vp)]
+    L.afsk_rx_plan_reset.argtypes = [vp, C.c_int, i64p, i64p, i32p, i32p]
+    L.afsk_rx_plan_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.afsk_rx_host_release.argtypes = [C.c_int]
     L.afsk_rx_plan_destroy.argtypes = [vp]
     L.afsk_rx_plan_out_offsets.argtypes = [vp, C.POINTER(i64p)]
     L.afsk_rx_plan_launches.argtypes = [vp, C.POINTER(C.c_int)]
@@ -146,12 +150,16 @@ class DeviceBuffer:
 
     def upload(self, arr: np.ndarray, stream=None, offset: int = 0):
         arr = np.ascontiguousarray(arr)
-        assert offset + arr.nbytes <= max(self.nbytes, 16)
+        if offset < 0 or offset + arr.nbytes > max(self.nbytes, 16):
+            raise ValueError(f"upload of {arr.nbytes} bytes at offset {offset} exceeds the {self.nbytes}-byte device buffer")
         check(lib().afsk_memcpy_h2d(self.device, C.c_void_p(self.ptr + offset), C.c_void_p(arr.ctypes.data),
                                     arr.nbytes, C.c_void_p(stream or 0)))
 
     def download(self, arr: np.ndarray, stream=None, offset: int = 0):
-        assert arr.flags["C_CONTIGUOUS"] and offset + arr.nbytes <= max(self.nbytes, 16)
+        if not arr.flags["C_CONTIGUOUS"]:
+            raise ValueError("download target must be C-contiguous")
+        if offset < 0 or offset + arr.nbytes > max(self.nbytes, 16):
+            raise ValueError(f"download of {arr.nbytes} bytes at offset {offset} exceeds the {self.nbytes}-byte device buffer")
         check(lib().afsk_memcpy_d2h(self.device, C.c_void_p(arr.ctypes.data), C.c_void_p(self.ptr + offset),
                                     arr.nbytes, C.c_void_p(stream or 0)))
 

@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <new>
 #include <utility>
 #include <vector>
@@ -1399,7 +1400,7 @@ struct Group {
     size_t smem = 0;
     int grid = 0;
     std::vector<int32_t> caps, tile_first, tile_gpos;
-    int32_t *d_caps = nullptr, *d_tile_first = nullptr, *d_tile_gpos = nullptr;
+    int32_t *d_caps = nullptr, *d_tile_first = nullptr, *d_tile_gpos = nullptr;   // inside the plan's arena
 };
 
 }  // namespace
@@ -1441,6 +1442,11 @@ struct AfskRxPlan {
     std::vector<CapDesc> caps;
     std::vector<int64_t> out_off;
     std::vector<Group> groups;
+    // ONE device allocation (grow-only, reused by afsk_rx_plan_reset): descriptor block (capture
+    // descriptors, then every group's capture list / tile prefix / tile map), clock indices, bit planes
+    uint8_t *arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<uint8_t> h_desc;  // host image of the descriptor block: one H2D copy per (re)build
     CapDesc *d_caps = nullptr;
     int32_t *d_clock = nullptr;
     uint2 *d_planes = nullptr;
@@ -1448,6 +1454,8 @@ struct AfskRxPlan {
     int64_t max_windows = 0;
     int64_t sum_windows = 0;      // over the captures decoded on the GPU
     int64_t gpu_caps = 0;
+    int frame_kernel = 0;         // AFSK_OPT_FRAME_KERNEL: 0 automatic, 1 k_frame_warp, 2 k_frame<128,4,int>, 3 <512,8,int>, 4 <512,8,long long>
+    int l2_hint = -1;             // AFSK_OPT_L2_HINT / AFSK_L2_HINT (read once per plan): -1 per-kernel default
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
 };
@@ -1570,6 +1578,132 @@ static int gate_run(int device, const int16_t *d_samples, const int64_t *h_offse
     return AFSK_OK;
 }
 
+// (Re)builds every host- and device-side descriptor of a plan for a batch layout.  The device arena is
+// reused when it is large enough (grow-only), so re-targeting a plan costs one H2D copy of the
+// descriptor block and no allocation.
+static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_t *h_len, const int32_t *h_baud,
+                      const int32_t *h_amp_end)
+{
+    P->B = B;
+    P->caps.assign((size_t)B, CapDesc());
+    P->out_off.assign((size_t)B + 1, 0);
+    P->groups.clear();
+    P->max_windows = P->sum_windows = P->gpu_caps = 0;
+    std::map<int, int> bf_to_group;
+    int64_t words = 0;
+    for (int c = 0; c < B; c++) {
+        CapDesc &d = P->caps[c];
+        d.off = h_start[c];
+        d.n = h_len[c];
+        if (d.n < 0 || d.off < 0) { afsk_set_error("capture %d: negative start or length (offsets must be non-decreasing)", c); return AFSK_E_ARG; }
+        d.plane_base = words;
+        d.out_off = P->out_off[c];
+        d.group = -1;
+        int bf = 0, ml = 0, sl = 0;
+        long long thr = h_amp_end[c];
+        d.thr = (int32_t)std::min<long long>(std::max<long long>(thr, 0), 65537);
+        if (!afsk_tone_geometry(h_baud[c], &bf, &ml, &sl)) {
+            d.bf = 0; d.status0 = AFSK_ST_EXC_BAUD;
+        } else {
+            d.bf = bf;
+            if (d.n < AFSK_SYNC_FRAMES) d.status0 = AFSK_ST_NO_CLOCK;                 // :323-325
+            else if (AFSK_SYNC_FRAMES - 2 * bf <= 0) d.status0 = AFSK_ST_EXC_INDEX;   // :332 on []
+            else if (ml != bf || sl != bf) d.status0 = AFSK_ST_EXC_WAVELEN;           // :102-103
+            else d.status0 = 0;
+        }
+        int64_t cap_bytes = 16;
+        if (d.status0 == 0) {
+            auto it = bf_to_group.find(bf);
+            if (it == bf_to_group.end()) {
+                Group g;
+                if (!configure_group(g, bf)) { afsk_set_error("bit_frames %d needs too much shared memory", bf); return AFSK_E_UNSUPPORTED; }
+                g.tile_first.push_back(0);
+                P->groups.push_back(g);
+                it = bf_to_group.emplace(bf, (int)P->groups.size() - 1).first;
+            }
+            Group &g = P->groups[it->second];
+            d.group = it->second;
+            const int64_t kmax = (d.n - bf + bf - 1) / bf;             // windows at clock 0
+            const int64_t ntiles = (kmax + g.wt - 1) / g.wt;
+            P->max_windows = std::max(P->max_windows, kmax);
+            P->sum_windows += kmax;
+            P->gpu_caps++;
+            if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { afsk_set_error("batch too large"); return AFSK_E_ARG; }
+            g.caps.push_back(c);
+            g.tile_gpos.insert(g.tile_gpos.end(), (size_t)ntiles, (int32_t)g.caps.size() - 1);
+            g.tile_first.push_back(g.tile_first.back() + (int32_t)ntiles);
+            words += ntiles * (g.wt / 32) + 4;
+            cap_bytes = (kmax / 14 + 16 + 15) & ~(int64_t)15;
+        }
+        P->out_off[c + 1] = P->out_off[c] + cap_bytes;
+    }
+    P->plane_words = words + 8;
+
+    // ---- descriptor block image (every sub-array 16-byte aligned) ----
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t desc_bytes = align16(sizeof(CapDesc) * (size_t)B);
+    std::vector<size_t> goff;
+    for (Group &g : P->groups) {
+        goff.push_back(desc_bytes); desc_bytes += align16(sizeof(int32_t) * g.caps.size());
+        goff.push_back(desc_bytes); desc_bytes += align16(sizeof(int32_t) * g.tile_first.size());
+        goff.push_back(desc_bytes); desc_bytes += align16(sizeof(int32_t) * g.tile_gpos.size());
+    }
+    desc_bytes = (desc_bytes + 255) & ~(size_t)255;
+    const size_t clock_off = desc_bytes;
+    const size_t planes_off = clock_off + ((sizeof(int32_t) * (size_t)(B ? B : 1) + 255) & ~(size_t)255);
+    const size_t need = planes_off + sizeof(uint2) * (size_t)P->plane_words;
+    P->h_desc.assign(desc_bytes, 0);
+    if (B) memcpy(P->h_desc.data(), P->caps.data(), sizeof(CapDesc) * (size_t)B);
+    for (size_t gi = 0; gi < P->groups.size(); gi++) {
+        Group &g = P->groups[gi];
+        memcpy(P->h_desc.data() + goff[3 * gi], g.caps.data(), sizeof(int32_t) * g.caps.size());
+        memcpy(P->h_desc.data() + goff[3 * gi + 1], g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());
+        memcpy(P->h_desc.data() + goff[3 * gi + 2], g.tile_gpos.data(), sizeof(int32_t) * g.tile_gpos.size());
+        g.tile_gpos.clear(); g.tile_gpos.shrink_to_fit();
+    }
+    cudaError_t e = cudaSuccess;
+    if (need > P->arena_bytes) {
+        const bool regrow = P->arena != nullptr;
+        if (P->arena) cudaFree(P->arena);
+        P->arena = nullptr;
+        P->arena_bytes = 0;
+        const size_t want = regrow ? need + need / 4 : need;        // a plan that is being re-targeted: head-room for the next layout
+        e = cudaMalloc((void **)&P->arena, want);
+        if (e == cudaSuccess) {
+            P->arena_bytes = want;
+            // k_frame may load (and mask / shift out) plane words past a capture's last window: keep them
+            // defined.  Stale words of an earlier layout are as good as zeros for that purpose.
+            e = cudaMemsetAsync(P->arena, 0, want, 0);
+        }
+    }
+    if (e == cudaSuccess && desc_bytes) e = cudaMemcpyAsync(P->arena, P->h_desc.data(), desc_bytes, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) {
+        P->d_caps = reinterpret_cast<CapDesc *>(P->arena);
+        P->d_clock = reinterpret_cast<int32_t *>(P->arena + clock_off);
+        P->d_planes = reinterpret_cast<uint2 *>(P->arena + planes_off);
+        for (size_t gi = 0; gi < P->groups.size(); gi++) {
+            Group &g = P->groups[gi];
+            g.d_caps = reinterpret_cast<int32_t *>(P->arena + goff[3 * gi]);
+            g.d_tile_first = reinterpret_cast<int32_t *>(P->arena + goff[3 * gi + 1]);
+            g.d_tile_gpos = reinterpret_cast<int32_t *>(P->arena + goff[3 * gi + 2]);
+            const int total = g.tile_first.back();
+            // two CTAs per SM even where three would fit: measured on one box, 3 CTAs per SM give 6223 GB/s
+            // against 7115 at 1200 baud and 5663 against 6610 at 300 baud (profiles/r1_tuning_log.md)
+            const int per_sm = g.smem <= 113 * 1024 ? 2 : 1;
+            g.grid = std::max(1, std::min(total, P->sm_count * per_sm));
+        }
+        static bool attr_set[64] = {};
+        if (P->device < 0 || P->device >= 64 || !attr_set[P->device]) {
+            e = demod_set_smem_attr();
+            if (e == cudaSuccess && P->device >= 0 && P->device < 64) attr_set[P->device] = true;
+        }
+    }
+    // the set-up ran on the legacy default stream; decodes may use non-blocking streams
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) { afsk_set_error("afsk_rx_plan: %s", cudaGetErrorString(e)); return AFSK_E_CUDA; }
+    return AFSK_OK;
+}
+
 extern "C" {
 
 int64_t afsk_rx_out_capacity(int64_t n_samples, int baud)
@@ -1603,90 +1737,36 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     AfskRxPlan *P = new (std::nothrow) AfskRxPlan();
     if (!P) return AFSK_E_ARG;
     P->device = device;
-    P->B = B;
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) P->sm_count = sms;
-    P->caps.resize(B);
-    P->out_off.assign(B + 1, 0);
-    std::map<int, int> bf_to_group;
-    int64_t words = 0;
-    for (int c = 0; c < B; c++) {
-        CapDesc &d = P->caps[c];
-        d.off = h_start[c];
-        d.n = h_len[c];
-        if (d.n < 0 || d.off < 0) { delete P; afsk_set_error("capture %d: negative start or length (offsets must be non-decreasing)", c); return AFSK_E_ARG; }
-        d.plane_base = words;
-        d.out_off = P->out_off[c];
-        d.group = -1;
-        int bf = 0, ml = 0, sl = 0;
-        long long thr = h_amp_end[c];
-        d.thr = (int32_t)std::min<long long>(std::max<long long>(thr, 0), 65537);
-        if (!afsk_tone_geometry(h_baud[c], &bf, &ml, &sl)) {
-            d.bf = 0; d.status0 = AFSK_ST_EXC_BAUD;
-        } else {
-            d.bf = bf;
-            if (d.n < AFSK_SYNC_FRAMES) d.status0 = AFSK_ST_NO_CLOCK;                 // :323-325
-            else if (AFSK_SYNC_FRAMES - 2 * bf <= 0) d.status0 = AFSK_ST_EXC_INDEX;   // :332 on []
-            else if (ml != bf || sl != bf) d.status0 = AFSK_ST_EXC_WAVELEN;           // :102-103
-            else d.status0 = 0;
-        }
-        int64_t cap_bytes = 16;
-        if (d.status0 == 0) {
-            auto it = bf_to_group.find(bf);
-            if (it == bf_to_group.end()) {
-                Group g;
-                if (!configure_group(g, bf)) { delete P; afsk_set_error("bit_frames %d needs too much shared memory", bf); return AFSK_E_UNSUPPORTED; }
-                g.tile_first.push_back(0);
-                P->groups.push_back(g);
-                it = bf_to_group.emplace(bf, (int)P->groups.size() - 1).first;
-            }
-            Group &g = P->groups[it->second];
-            d.group = it->second;
-            const int64_t kmax = (d.n - bf + bf - 1) / bf;             // windows at clock 0
-            const int64_t ntiles = (kmax + g.wt - 1) / g.wt;
-            P->max_windows = std::max(P->max_windows, kmax);
-            P->sum_windows += kmax;
-            P->gpu_caps++;
-            if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { delete P; afsk_set_error("batch too large"); return AFSK_E_ARG; }
-            g.caps.push_back(c);
-            g.tile_gpos.insert(g.tile_gpos.end(), (size_t)ntiles, (int32_t)g.caps.size() - 1);
-            g.tile_first.push_back(g.tile_first.back() + (int32_t)ntiles);
-            words += ntiles * (g.wt / 32) + 4;
-            cap_bytes = (kmax / 14 + 16 + 15) & ~(int64_t)15;
-        }
-        P->out_off[c + 1] = P->out_off[c] + cap_bytes;
-    }
-    P->plane_words = words + 8;
-    cudaError_t e = cudaSuccess;
-    auto up = [&](void **dptr, const void *src, size_t bytes) {
-        if (e != cudaSuccess) return;
-        e = cudaMalloc(dptr, bytes ? bytes : 16);
-        if (e == cudaSuccess && bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
-    };
-    up((void **)&P->d_caps, P->caps.data(), sizeof(CapDesc) * B);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_clock, sizeof(int32_t) * (B ? B : 1));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&P->d_planes, sizeof(uint2) * P->plane_words);
-    // k_frame may load (and mask / shift out) plane words past a capture's last window: keep them defined
-    if (e == cudaSuccess) e = cudaMemset(P->d_planes, 0, sizeof(uint2) * P->plane_words);
-    for (Group &g : P->groups) {
-        up((void **)&g.d_caps, g.caps.data(), sizeof(int32_t) * g.caps.size());
-        up((void **)&g.d_tile_first, g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());
-        up((void **)&g.d_tile_gpos, g.tile_gpos.data(), sizeof(int32_t) * g.tile_gpos.size());
-        g.tile_gpos.clear(); g.tile_gpos.shrink_to_fit();
-        const int total = g.tile_first.back();
-        // two CTAs per SM even where three would fit: measured on one box, 3 CTAs per SM give 6223 GB/s
-        // against 7115 at 1200 baud and 5663 against 6610 at 300 baud (profiles/r1_tuning_log.md)
-        const int per_sm = g.smem <= 113 * 1024 ? 2 : 1;
-        g.grid = std::max(1, std::min(total, P->sm_count * per_sm));
-    }
-    if (e == cudaSuccess) e = demod_set_smem_attr();
-    if (e != cudaSuccess) {
-        afsk_set_error("afsk_rx_plan_create: %s", cudaGetErrorString(e));
-        afsk_rx_plan_destroy(P);
-        return AFSK_E_CUDA;
-    }
+    const char *ev = getenv("AFSK_L2_HINT");            // tuning override, read once per plan
+    if (ev) P->l2_hint = atoi(ev);
+    const int rc = plan_build(P, B, h_start, h_len, h_baud, h_amp_end);
+    if (rc != AFSK_OK) { afsk_rx_plan_destroy(P); return rc; }
     *plan_out = P;
     return AFSK_OK;
+}
+
+int afsk_rx_plan_reset(AfskRxPlan *P, int B, const int64_t *h_start, const int64_t *h_len, const int32_t *h_baud,
+                       const int32_t *h_amp_end)
+{
+    if (!P || B < 0 || (B > 0 && (!h_start || !h_baud || !h_amp_end))) {
+        afsk_set_error("afsk_rx_plan_reset: bad argument");
+        return AFSK_E_ARG;
+    }
+    AfskDeviceGuard guard(P->device);
+    if (!guard.ok) { afsk_set_error("cannot select device %d", P->device); return AFSK_E_CUDA; }
+    std::vector<int64_t> len;
+    if (!h_len) {                                        // CSR offsets (B + 1)
+        len.resize((size_t)B);
+        for (int c = 0; c < B; c++) len[c] = h_start[c + 1] - h_start[c];
+        h_len = len.data();
+    }
+    for (auto &ev : P->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    P->timing_events.clear();
+    const int rc = plan_build(P, B, h_start, h_len, h_baud, h_amp_end);
+    if (rc != AFSK_OK) { P->B = 0; P->groups.clear(); }  // unusable until the next successful reset
+    return rc;
 }
 
 int afsk_rx_plan_destroy(AfskRxPlan *P)
@@ -1694,10 +1774,26 @@ int afsk_rx_plan_destroy(AfskRxPlan *P)
     if (!P) return AFSK_OK;
     AfskDeviceGuard guard(P->device);
     for (auto &ev : P->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    cudaFree(P->d_caps); cudaFree(P->d_clock); cudaFree(P->d_planes);
-    for (Group &g : P->groups) { cudaFree(g.d_caps); cudaFree(g.d_tile_first); cudaFree(g.d_tile_gpos); }
+    cudaFree(P->arena);
     delete P;
     return AFSK_OK;
+}
+
+int afsk_rx_plan_set_option(AfskRxPlan *P, int option, int value)
+{
+    if (!P) return AFSK_E_ARG;
+    switch (option) {
+    case AFSK_OPT_FRAME_KERNEL:
+        if (value < 0 || value > 4) { afsk_set_error("AFSK_OPT_FRAME_KERNEL: 0..4"); return AFSK_E_ARG; }
+        P->frame_kernel = value;
+        return AFSK_OK;
+    case AFSK_OPT_L2_HINT:
+        P->l2_hint = value < 0 ? -1 : (value ? 1 : 0);
+        return AFSK_OK;
+    default:
+        afsk_set_error("afsk_rx_plan_set_option: unknown option %d", option);
+        return AFSK_E_ARG;
+    }
 }
 
 int afsk_rx_plan_out_offsets(const AfskRxPlan *P, const int64_t **h_out_off)
@@ -1771,9 +1867,9 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         p.stage_bytes = g.stage_bytes; p.stages = g.stages;
         // L2 evict-first on the bulk copies (the samples are read once).  Same-box A/B: k_demod +2-6 %
         // (c2 0.768 -> 0.745 ms, 600 baud 0.819 -> 0.770), k_demod_shift +1-2.5 %, the short-window kernel 0 to -10 %
-        // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 forces.
-        const int l2_force = getenv("AFSK_L2_HINT") ? atoi(getenv("AFSK_L2_HINT")) : -1;
-        p.l2_hint = l2_force >= 0 ? l2_force : (g.small_wpt ? 0 : 1);
+        // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 (environment, read at
+        // plan creation) or AFSK_OPT_L2_HINT force it.
+        p.l2_hint = P->l2_hint >= 0 ? P->l2_hint : (g.small_wpt ? 0 : 1);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
@@ -1788,12 +1884,23 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
             P->timing_events.emplace_back(e0, e1);
         }
     }
-    if (P->max_windows <= kFrameWarpMaxWindows)
+    // framing kernel: automatic by capture length, or forced (AFSK_OPT_FRAME_KERNEL) where the forced variant can
+    // represent the batch (k_frame_warp: <= 2^18 windows per capture; int indices: < 2^30)
+    int fk = P->frame_kernel;
+    if (fk == 1 && P->max_windows > kFrameWarpMaxWindows) fk = 0;
+    if ((fk == 2 || fk == 3) && P->max_windows >= ((int64_t)1 << 30)) fk = 0;
+    if (fk == 0) {
+        if (P->max_windows <= kFrameWarpMaxWindows) fk = 1;
+        else if (P->max_windows >= ((int64_t)1 << 30)) fk = 4;
+        else if (P->sum_windows > 65536 * std::max<int64_t>(P->gpu_caps, 1)) fk = 3;   // long captures on average
+        else fk = 2;
+    }
+    if (fk == 1)
         k_frame_warp<<<(P->B + kFrameWarpCaps - 1) / kFrameWarpCaps, 32 * kFrameWarpCaps, 0, st>>>(P->d_caps, P->d_clock, P->d_planes,
                                                                                                  d_out, d_res, P->B);
-    else if (P->max_windows >= ((int64_t)1 << 30))
+    else if (fk == 4)
         k_frame<512, 8, long long><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
-    else if (P->sum_windows > 65536 * std::max<int64_t>(P->gpu_caps, 1))   // long captures on average
+    else if (fk == 3)
         k_frame<512, 8, int><<<P->B, 512, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
     else
         k_frame<128, 4, int><<<P->B, 128, 0, st>>>(P->d_caps, P->d_clock, P->d_planes, d_out, d_res);
@@ -1801,47 +1908,98 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     return AFSK_OK;
 }
 
+// afsk_rx_decode_host keeps one plan and one set of grow-only device / pinned buffers per device between
+// calls (a drop-in Receiver.load calls it once per file): after the first call a decode costs the two
+// copies and three launches, no allocation.  Calls on the same device are serialised by the context's mutex.
+namespace {
+struct HostCtx {
+    std::mutex m;
+    AfskRxPlan *plan = nullptr;
+    int16_t *d_samples = nullptr; size_t samples_cap = 0;
+    uint8_t *d_out = nullptr; size_t out_cap = 0;
+    AfskRxResult *d_res = nullptr; size_t res_cap = 0;
+    uint8_t *h_stage = nullptr; size_t stage_cap = 0;      // pinned: results, then the payload blob
+};
+HostCtx g_host_ctx[64];
+
+cudaError_t grow_device(void **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4 + 4096;
+    const cudaError_t e = cudaMalloc(p, want);
+    if (e == cudaSuccess) *cap = want;
+    return e;
+}
+}  // namespace
+
 int afsk_rx_decode_host(int device, const int16_t *h_samples, const int64_t *h_offsets, int B, const int32_t *h_baud,
                         const int32_t *h_amp_end, uint8_t *h_out, const int64_t *h_out_off, AfskRxResult *h_res)
 {
     if (B < 0 || (B > 0 && (!h_samples || !h_offsets || !h_out || !h_out_off || !h_res))) return AFSK_E_ARG;
     if (B == 0) return AFSK_OK;
-    AfskRxPlan *P = nullptr;
-    int rc = afsk_rx_plan_create(device, B, h_offsets, h_baud, h_amp_end, &P);
+    if (device < 0 || device >= 64) { afsk_set_error("afsk_rx_decode_host: device %d out of range", device); return AFSK_E_ARG; }
+    HostCtx &X = g_host_ctx[device];
+    std::lock_guard<std::mutex> lock(X.m);
+    int rc;
+    if (!X.plan) rc = afsk_rx_plan_create(device, B, h_offsets, h_baud, h_amp_end, &X.plan);
+    else rc = afsk_rx_plan_reset(X.plan, B, h_offsets, nullptr, h_baud, h_amp_end);
     if (rc) return rc;
+    AfskRxPlan *P = X.plan;
     AfskDeviceGuard guard(device);
     const int64_t total = h_offsets[B], base = h_offsets[0] & ~(int64_t)7;
     const size_t sample_bytes = (size_t)(((total - base) * 2 + 15) & ~(int64_t)15) + 16;
-    int16_t *d_samples = nullptr; uint8_t *d_out = nullptr; AfskRxResult *d_res = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_samples, sample_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (size_t)P->out_off[B]);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_res, sizeof(AfskRxResult) * B);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_samples, h_samples + base, (size_t)(total - base) * 2, cudaMemcpyHostToDevice, 0);
+    const size_t out_bytes = (size_t)P->out_off[B], res_bytes = sizeof(AfskRxResult) * (size_t)B;
+    cudaError_t e = grow_device((void **)&X.d_samples, &X.samples_cap, sample_bytes);
+    if (e == cudaSuccess) e = grow_device((void **)&X.d_out, &X.out_cap, out_bytes);
+    if (e == cudaSuccess) e = grow_device((void **)&X.d_res, &X.res_cap, res_bytes);
+    if (e == cudaSuccess && res_bytes + out_bytes > X.stage_cap) {
+        if (X.h_stage) cudaFreeHost(X.h_stage);
+        X.h_stage = nullptr; X.stage_cap = 0;
+        const size_t want = (res_bytes + out_bytes) * 5 / 4 + 4096;
+        e = cudaMallocHost((void **)&X.h_stage, want);
+        if (e == cudaSuccess) X.stage_cap = want;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(X.d_samples, h_samples + base, (size_t)(total - base) * 2, cudaMemcpyHostToDevice, 0);
     if (e == cudaSuccess) {
         // the plan indexes samples from global sample 0: pass the shifted base pointer
-        rc = afsk_rx_decode(P, d_samples - base, d_out, d_res, nullptr);
+        rc = afsk_rx_decode(P, X.d_samples - base, X.d_out, X.d_res, nullptr);
         if (rc == AFSK_OK) {
-            e = cudaMemcpyAsync(h_res, d_res, sizeof(AfskRxResult) * B, cudaMemcpyDeviceToHost, 0);
+            AfskRxResult *sr = reinterpret_cast<AfskRxResult *>(X.h_stage);
+            uint8_t *sb = X.h_stage + res_bytes;
+            e = cudaMemcpyAsync(sr, X.d_res, res_bytes, cudaMemcpyDeviceToHost, 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(sb, X.d_out, out_bytes, cudaMemcpyDeviceToHost, 0);
             if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-            // compact copy-back: only the decoded bytes of each capture
-            std::vector<uint8_t> tmp;
             if (e == cudaSuccess) {
-                tmp.resize((size_t)P->out_off[B]);
-                e = cudaMemcpy(tmp.data(), d_out, tmp.size(), cudaMemcpyDeviceToHost);
-            }
-            if (e == cudaSuccess) {
+                memcpy(h_res, sr, res_bytes);
+                // compact copy-back: only the decoded bytes of each capture
                 for (int c = 0; c < B; c++) {
-                    int64_t nb = h_res[c].nbytes, cap = h_out_off[c + 1] - h_out_off[c];
+                    int64_t nb = sr[c].nbytes, cap = h_out_off[c + 1] - h_out_off[c];
                     if (nb > cap) { rc = AFSK_E_ARG; afsk_set_error("output capacity too small for capture %d", c); break; }
-                    if (nb > 0) memcpy(h_out + h_out_off[c], tmp.data() + P->out_off[c], (size_t)nb);
+                    if (nb > 0) memcpy(h_out + h_out_off[c], sb + P->out_off[c], (size_t)nb);
                 }
             }
         }
     }
-    cudaFree(d_samples); cudaFree(d_out); cudaFree(d_res);
-    afsk_rx_plan_destroy(P);
     if (e != cudaSuccess) { afsk_set_error("afsk_rx_decode_host: %s", cudaGetErrorString(e)); return AFSK_E_CUDA; }
     return rc;
+}
+
+/* releases what afsk_rx_decode_host keeps per device between calls */
+int afsk_rx_host_release(int device)
+{
+    if (device < 0 || device >= 64) return AFSK_E_ARG;
+    HostCtx &X = g_host_ctx[device];
+    std::lock_guard<std::mutex> lock(X.m);
+    AfskDeviceGuard guard(device);
+    if (X.plan) afsk_rx_plan_destroy(X.plan);
+    X.plan = nullptr;
+    cudaFree(X.d_samples); cudaFree(X.d_out); cudaFree(X.d_res);
+    if (X.h_stage) cudaFreeHost(X.h_stage);
+    X.d_samples = nullptr; X.d_out = nullptr; X.d_res = nullptr; X.h_stage = nullptr;
+    X.samples_cap = X.out_cap = X.res_cap = X.stage_cap = 0;
+    return AFSK_OK;
 }
 
 int afsk_rx_gate(int device, const int16_t *d_samples, const int64_t *h_offsets, int S, int amp_start, int amp_end,

@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import ctypes as C
 import wave
-import weakref
 from datetime import datetime
 
 import numpy as np
@@ -118,6 +117,34 @@ class ECC:
         return "".join(out)
 
 
+class SoundInput:
+    """File half of the reference's SoundInput (afskmodem.py:180-221).  ``loadFromFile`` is the static
+    helper ``Receiver.load`` uses (:213-217); the pyaudio stream methods need an audio device and raise."""
+
+    def __init__(self):
+        raise RuntimeError("afskmodem_b200 has no live audio input; SoundInput.loadFromFile is available")
+
+    @staticmethod
+    def loadFromFile(filename: str) -> list[int]:
+        return read_wav_frames(filename).tolist()
+
+
+class SoundOutput:
+    """File half of the reference's SoundOutput (afskmodem.py:226-268): ``writeToFile`` with
+    ``__convertFrames``' pair duplication (out[n] = frames[n & ~1], an odd last frame dropped, :239-244)."""
+
+    def __init__(self):
+        raise RuntimeError("afskmodem_b200 has no live audio output; SoundOutput.writeToFile is available")
+
+    @staticmethod
+    def writeToFile(filename: str, frames) -> None:
+        f = np.asarray(frames, dtype=np.int64)
+        even = f[0:len(f) - 1:2]
+        if len(even) and (even.min() < -32768 or even.max() > 32767):
+            raise OverflowError("int too big to convert")            # int.to_bytes(2, signed=True) :242
+        write_wav_frames(filename, np.repeat(even.astype(np.int16), 2))
+
+
 def _check_baud(baud_rate) -> int:
     """Constructor-time validation with the reference's exceptions (afskmodem.py:69-70, 81-83)."""
     Waveforms.getSpaceTone(baud_rate)      # raises Exception("Invalid baud rate.") / ZeroDivisionError
@@ -177,42 +204,69 @@ class RxSession:
         """``offsets``: CSR offsets (B+1) of adjacent captures, or — with ``lengths`` (B) — the start of
         each capture inside one sample buffer (captures need not be adjacent)."""
         _cabi.require_device(device)
-        L = _cabi.lib()
         self.device = device
+        self.plan = None
+        self._destroy = _cabi.lib().afsk_rx_plan_destroy      # kept for close() during interpreter shutdown
+        self.d_out = self.d_res = self.d_samples = None
+        self._ext_ptr = None
+        self._configure(offsets, baud, amp_end, lengths)
+
+    def reset(self, offsets, baud, amp_end, lengths=None):
+        """Re-targets this session at another batch layout (``afsk_rx_plan_reset``): the plan's device
+        arena and this session's buffers are reused when large enough, so a receiver that decodes one
+        file after another (``Receiver.load``) allocates nothing after its first calls."""
+        self._configure(offsets, baud, amp_end, lengths)
+
+    def _configure(self, offsets, baud, amp_end, lengths):
+        L = _cabi.lib()
+        device = self.device
         self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self.lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int64)
         self.B = len(self.offsets) - 1 if self.lengths is None else len(self.lengths)
+        if self.lengths is not None and len(self.offsets) != self.B:
+            raise ValueError("offsets (capture starts) and lengths must have one entry per capture")
         self.baud = np.ascontiguousarray(np.broadcast_to(np.asarray(baud, dtype=np.int32), (self.B,)))
         self.amp_end = np.ascontiguousarray(np.broadcast_to(np.asarray(amp_end, dtype=np.int32), (self.B,)))
-        plan = C.c_void_p()
-        if self.lengths is None:
-            _cabi.check(L.afsk_rx_plan_create(device, self.B, _cabi.ptr(self.offsets, C.c_int64),
-                                              _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
-                                              C.byref(plan)))
+        lens_p = None if self.lengths is None else _cabi.ptr(self.lengths, C.c_int64)
+        if self.plan is None:
+            plan = C.c_void_p()
+            if self.lengths is None:
+                _cabi.check(L.afsk_rx_plan_create(device, self.B, _cabi.ptr(self.offsets, C.c_int64),
+                                                  _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
+                                                  C.byref(plan)))
+            else:
+                _cabi.check(L.afsk_rx_plan_create_ranges(device, self.B, _cabi.ptr(self.offsets, C.c_int64), lens_p,
+                                                         _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
+                                                         C.byref(plan)))
+            self.plan = plan
         else:
-            assert len(self.offsets) == self.B
-            _cabi.check(L.afsk_rx_plan_create_ranges(device, self.B, _cabi.ptr(self.offsets, C.c_int64),
-                                                     _cabi.ptr(self.lengths, C.c_int64),
-                                                     _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32),
-                                                     C.byref(plan)))
-        self.plan = plan
-        self._destroy = L.afsk_rx_plan_destroy               # kept for close() during interpreter shutdown
+            _cabi.check(L.afsk_rx_plan_reset(self.plan, self.B, _cabi.ptr(self.offsets, C.c_int64), lens_p,
+                                             _cabi.ptr(self.baud, C.c_int32), _cabi.ptr(self.amp_end, C.c_int32)))
         po = C.POINTER(C.c_int64)()
-        _cabi.check(L.afsk_rx_plan_out_offsets(plan, C.byref(po)))
+        _cabi.check(L.afsk_rx_plan_out_offsets(self.plan, C.byref(po)))
         self.out_off = np.ctypeslib.as_array(po, shape=(self.B + 1,)).copy()
         n = C.c_int(0)
-        _cabi.check(L.afsk_rx_plan_launches(plan, C.byref(n)))
+        _cabi.check(L.afsk_rx_plan_launches(self.plan, C.byref(n)))
         self.launches = n.value
         if self.lengths is None:
             self.total_samples = int(self.offsets[-1])
         else:
             self.total_samples = int((self.offsets + self.lengths).max()) if self.B else 0
-        self.d_out = DeviceBuffer(device, int(self.out_off[-1]))
-        self.d_res = DeviceBuffer(device, 32 * max(self.B, 1))
-        # payloads are written at capacity offsets: keep the gaps between them defined (zero)
-        _cabi.check(L.afsk_memset(device, C.c_void_p(self.d_out.ptr), 0, max(int(self.out_off[-1]), 16), None))
-        self.d_samples = None
-        self._ext_ptr = None
+        out_bytes, res_bytes = int(self.out_off[-1]), 32 * max(self.B, 1)
+        if self.d_out is None or self.d_out.nbytes < out_bytes:
+            regrow = self.d_out is not None
+            if regrow:
+                self.d_out.close()
+            self.d_out = DeviceBuffer(device, out_bytes + (out_bytes // 4 if regrow else 0))
+            # payloads are written at capacity offsets: keep the gaps between them defined (zero; stale bytes
+            # of an earlier layout after a reset are as good)
+            _cabi.check(L.afsk_memset(device, C.c_void_p(self.d_out.ptr), 0, max(self.d_out.nbytes, 16), None))
+            _cabi.stream_sync(device)
+        if self.d_res is None or self.d_res.nbytes < res_bytes:
+            regrow = self.d_res is not None
+            if regrow:
+                self.d_res.close()
+            self.d_res = DeviceBuffer(device, res_bytes + (res_bytes // 4 if regrow else 0))
 
     def close(self):
         if getattr(self, "plan", None):
@@ -227,14 +281,30 @@ class RxSession:
 
     def upload(self, samples: np.ndarray, stream=None):
         samples = np.ascontiguousarray(samples, dtype=np.int16)
-        assert len(samples) >= self.total_samples
-        if self.d_samples is None:
-            self.d_samples = DeviceBuffer(self.device, (self.total_samples * 2 + 15) // 16 * 16 + 16)
+        if len(samples) < self.total_samples:
+            raise ValueError(f"samples holds {len(samples)} frames, the batch layout needs {self.total_samples}")
+        self.ensure_samples()
         self.d_samples.upload(samples[:self.total_samples], stream)
         self._ext_ptr = None
 
-    def bind(self, device_ptr: int):
-        """Use caller-owned device samples (16-byte aligned, padded to 16 bytes past the end)."""
+    def ensure_samples(self):
+        """The session's own device sample buffer, (re)allocated when the layout outgrew it."""
+        need = (self.total_samples * 2 + 15) // 16 * 16 + 16
+        if self.d_samples is None or self.d_samples.nbytes < need:
+            regrow = self.d_samples is not None
+            if regrow:
+                self.d_samples.close()
+            self.d_samples = DeviceBuffer(self.device, need + (need // 4 if regrow else 0))
+        return self.d_samples
+
+    def bind(self, device_ptr: int, nsamples: int | None = None):
+        """Use caller-owned device samples (16-byte aligned, padded to 16 bytes past the end).
+        ``nsamples``: frames the caller's buffer holds — checked against the batch layout so that a
+        short buffer is a Python error, not an out-of-bounds device read."""
+        if int(device_ptr) % 16:
+            raise ValueError("device sample pointer must be 16-byte aligned")
+        if nsamples is not None and int(nsamples) < self.total_samples:
+            raise ValueError(f"bound buffer holds {int(nsamples)} frames, the batch layout needs {self.total_samples}")
         self._ext_ptr = int(device_ptr)
 
     def run(self, stream=None):
@@ -305,11 +375,12 @@ class PipelinedRxSession:
         self.launches = sum(sess.launches for sess in self.sessions)
         # one host result set for the whole batch; every range downloads into its slice
         self.res_lo, self.blob_lo, self.out_off = self.merged_layout([sess.out_off for sess in self.sessions])
-        # pinned host result sets: the D2H copies are truly asynchronous (range j's results travel while
-        # range j+1 is still uploading — the link is full duplex).  A set is re-used only once the RxBatch
-        # it was handed out in is gone (weak reference), so a caller that keeps batches never sees them change.
-        # Two sets exist from the start: a loop that rebinds its result variable alternates between them.
-        self._host = [self._new_host_set() for _ in range(2)]   # [(results, blob) PinnedArrays, weakref to the last RxBatch | None]
+        # pinned staging for the results: the D2H copies are truly asynchronous (range j's results travel
+        # while range j+1 is still uploading — the link is full duplex).  The batch handed to the caller
+        # OWNS its arrays (copied out of the staging set: ~0.1 % of the sample bytes), so a caller may keep
+        # any field view for as long as it likes while the staging set is reused by the next decode.
+        self._stage = (_cabi.PinnedArray((max(self.B, 1),), _cabi.RX_RESULT_DTYPE),
+                       _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8))
         _cabi.stream_sync(device)          # plan set-up (default stream) is complete before the side streams run
 
     @staticmethod
@@ -322,26 +393,12 @@ class PipelinedRxSession:
                                  [blob_lo[-1:]]).astype(np.int64)
         return res_lo, blob_lo, out_off
 
-    def _new_host_set(self):
-        return [(_cabi.PinnedArray((self.B,), _cabi.RX_RESULT_DTYPE),
-                 _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8)), None]
-
-    def _host_set(self):
-        for entry in self._host:
-            if entry[1] is None or entry[1]() is None:
-                return entry
-        entry = self._new_host_set()
-        if len(self._host) < 4:            # beyond that the set simply belongs to the batch that holds it
-            self._host.append(entry)
-        return entry
-
     def decode(self, samples: np.ndarray) -> RxBatch:
-        """The returned batch views pinned host memory that stays untouched for as long as the batch lives."""
+        """The returned batch owns its arrays (nothing in it aliases this session's buffers)."""
         samples = np.ascontiguousarray(samples, dtype=np.int16)
-        assert len(samples) >= self.total_samples
-        entry = self._host_set()
-        owner = entry[0]
-        res, blob = (h.array for h in owner)
+        if len(samples) < self.total_samples:
+            raise ValueError(f"samples holds {len(samples)} frames, the batch layout needs {self.total_samples}")
+        res, blob = (h.array for h in self._stage)
         for j, ((lo, hi), sess) in enumerate(zip(self.ranges, self.sessions)):
             a, b = int(self.offsets[lo]), int(self.offsets[hi])
             if b > a:
@@ -351,10 +408,7 @@ class PipelinedRxSession:
             sess.download(self.compute_stream, res[self.res_lo[j]:self.res_lo[j + 1]],
                           blob[self.blob_lo[j]:self.blob_lo[j + 1]], sync=False)
         _cabi.stream_sync(self.device, self.compute_stream)
-        out = RxBatch(res, blob[:int(self.blob_lo[-1])], self.out_off)
-        out._owner = owner                 # the pinned memory lives as long as a batch refers to it
-        entry[1] = weakref.ref(out)
-        return out
+        return RxBatch(res[:self.B].copy(), blob[:int(self.blob_lo[-1])].copy(), self.out_off)
 
     def close(self):
         for sess in getattr(self, "sessions", []):
@@ -368,7 +422,100 @@ class PipelinedRxSession:
             if st:
                 _cabi.stream_destroy(self.device, st)
                 setattr(self, name, None)
-        self._host = []                    # the pinned sets are freed when the last RxBatch viewing them is gone
+        for h in getattr(self, "_stage", ()):
+            h.close()
+        self._stage = ()
+
+    __del__ = close
+
+
+class ShardedRxSession:
+    """ONE corpus decoded on several GPUs from one process (captures are independent,
+    afskmodem.py:420-430, so there is no exchange step).
+
+    The corpus is cut into contiguous capture ranges balanced by predicted time
+    (``shard.capture_cost`` -> ``shard.shard_captures``), one per device.  Every device gets its own
+    host thread, streams and session over its range (a PipelinedRxSession when the range is large, so
+    its PCIe copy overlaps its kernels); the per-device results are gathered on the host into ONE
+    RxBatch in corpus order.  No collective touches the data path; ctypes releases the GIL during
+    every library call, so the device threads really run side by side."""
+
+    def __init__(self, offsets, baud, amp_end, devices, pipeline: int | None = None, weights=None):
+        from .shard import capture_cost, shard_captures
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise ValueError("devices must name at least one GPU")
+        for d in self.devices:
+            _cabi.require_device(d)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.B = len(self.offsets) - 1
+        self.total_samples = int(self.offsets[-1])
+        baud = np.ascontiguousarray(np.broadcast_to(np.asarray(baud, dtype=np.int32), (self.B,)))
+        amp_end = np.ascontiguousarray(np.broadcast_to(np.asarray(amp_end, dtype=np.int32), (self.B,)))
+        lengths = np.diff(self.offsets)
+        self.weights = capture_cost(lengths, baud, resident=False) if weights is None else np.asarray(weights, np.float64)
+        self.ranges = shard_captures(lengths, len(self.devices), self.weights)
+        self.sessions = []
+        for dev, (lo, hi) in zip(self.devices, self.ranges):
+            sub = self.offsets[lo:hi + 1] - self.offsets[lo]
+            nbytes = int(sub[-1]) * 2
+            k = pipeline
+            if k is None:
+                k = min(PIPELINE_CHUNKS, (hi - lo) // 4) if nbytes >= PIPELINE_MIN_BYTES else 1
+            if hi <= lo:
+                self.sessions.append(None)
+            elif k > 1:
+                self.sessions.append(PipelinedRxSession(sub, baud[lo:hi], amp_end[lo:hi], dev, k))
+            else:
+                self.sessions.append(RxSession(sub, baud[lo:hi], amp_end[lo:hi], dev))
+        self.launches = sum(s.launches for s in self.sessions if s is not None)
+        self.device_ms = [0.0] * len(self.devices)     # host wall time of every device's last decode
+
+    def _decode_one(self, j: int, samples: np.ndarray, out: list, errs: list):
+        import time
+        try:
+            t0 = time.perf_counter()
+            s = self.sessions[j]
+            lo, hi = self.ranges[j]
+            part = samples[int(self.offsets[lo]):int(self.offsets[hi])]
+            if s is None:
+                out[j] = None
+            elif isinstance(s, PipelinedRxSession):
+                out[j] = s.decode(part)
+            else:
+                s.upload(part)
+                s.run()
+                out[j] = s.download()
+            self.device_ms[j] = (time.perf_counter() - t0) * 1e3
+        except BaseException as e:  # noqa: BLE001 - re-raised on the calling thread
+            errs.append(e)
+
+    def decode(self, samples: np.ndarray) -> RxBatch:
+        import threading
+
+        from .shard import merge_rx_parts
+        samples = np.ascontiguousarray(samples, dtype=np.int16)
+        if len(samples) < self.total_samples:
+            raise ValueError(f"samples holds {len(samples)} frames, the batch layout needs {self.total_samples}")
+        out, errs = [None] * len(self.devices), []
+        threads = [threading.Thread(target=self._decode_one, args=(j, samples, out, errs)) for j in range(1, len(self.devices))]
+        for t in threads:
+            t.start()
+        self._decode_one(0, samples, out, errs)
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        parts = [(b.results, b.blob, b.out_off) for b in out if b is not None]
+        if not parts:
+            return RxBatch(np.zeros(0, dtype=_cabi.RX_RESULT_DTYPE), np.zeros(0, np.uint8), np.zeros(1, np.int64))
+        return RxBatch(*merge_rx_parts(parts))
+
+    def close(self):
+        for s in getattr(self, "sessions", []):
+            if s is not None:
+                s.close()
+        self.sessions = []
 
     __del__ = close
 
@@ -450,6 +597,29 @@ class WavBatch:
             self.errors[int(i)] = OSError(f"cannot read {self.filenames[i]!r}")
         return arr[:self.total]
 
+    def read_to_device(self, device: int, d_samples: DeviceBuffer, stream=None) -> None:
+        """Streams every file through the library's pinned staging ring straight into ``d_samples`` (same
+        CSR offsets): no host copy of the corpus is kept and nothing as large as the corpus is pinned, so
+        the first call of a process costs what later calls cost.  Returns once all samples are on the device."""
+        n = len(self)
+        if d_samples.nbytes < 2 * self.total:
+            raise ValueError(f"device buffer of {d_samples.nbytes} bytes cannot hold {self.total} samples")
+        ns = self.nsamples.copy()
+        for i in list(self.fallback) + list(self.errors):
+            ns[i] = 0                                   # not read natively (uploaded below / unreadable)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        _cabi.check(_cabi.lib().afsk_wav_load(self._paths, n, self.threads, _cabi.ptr(self.data_pos, C.c_int64),
+                                              _cabi.ptr(ns, C.c_int64), _cabi.ptr(self.offsets, C.c_int64),
+                                              None, device, C.c_void_p(d_samples.ptr), 0,
+                                              C.c_void_p(stream or 0), _cabi.ptr(st, C.c_int32)))
+        for i, fr in self.fallback.items():             # after the ring's copies: they cover these ranges too
+            if len(fr):
+                d_samples.upload(np.ascontiguousarray(fr, dtype=np.int16), stream, offset=2 * int(self.offsets[i]))
+        if self.fallback:
+            _cabi.stream_sync(device, stream)           # the fallback arrays are pageable host memory
+        for i in np.nonzero(st[:n])[0]:
+            self.errors[int(i)] = OSError(f"cannot read {self.filenames[i]!r}")
+
     def frames(self, i: int) -> np.ndarray:
         return self.array[self.offsets[i]:self.offsets[i + 1]]
 
@@ -470,10 +640,11 @@ class Receiver:
         self._log = Log("afskmodem.Receiver")
         self._cache = None                                       # (key, RxSession) of the last batch layout
 
-    def _session(self, offsets: np.ndarray, dev: int, baud=None, amp_end=None, chunks: int = 1):
+    def _session(self, offsets: np.ndarray, dev, baud=None, amp_end=None, chunks: int = 1):
         """Plan + device buffers are kept between calls with the same batch layout (like an FFT
         plan cache): repeated decode_batch calls then pay only H2D, kernels and D2H.
-        chunks > 1: a PipelinedRxSession (copy / compute overlap over capture ranges)."""
+        chunks > 1: a PipelinedRxSession (copy / compute overlap over capture ranges).
+        ``dev``: a device index, or a tuple of them (ShardedRxSession)."""
         baud = self._baud if baud is None else np.ascontiguousarray(baud, dtype=np.int32)
         amp_end = _as_int_threshold(self._amp_end) if amp_end is None else \
             np.ceil(np.asarray(amp_end, dtype=np.float64)).astype(np.int32)
@@ -481,16 +652,36 @@ class Receiver:
                amp_end if np.isscalar(amp_end) else amp_end.tobytes(), offsets.tobytes())
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1]
-        self.close()
-        s = RxSession(offsets, baud, amp_end, dev) if chunks <= 1 else PipelinedRxSession(offsets, baud, amp_end, dev, chunks)
+        cached = self._cache[1] if self._cache is not None else None
+        if type(cached) is RxSession and not isinstance(dev, tuple) and chunks <= 1 and cached.device == dev:
+            # same kind of session on the same GPU: re-target its plan and buffers instead of rebuilding them
+            self._cache = None
+            try:
+                cached.reset(offsets, baud, amp_end)
+            except Exception:
+                cached.close()
+                raise
+            self._cache = (key, cached)
+            return cached
+        self._drop_session()
+        if isinstance(dev, tuple):
+            s = ShardedRxSession(offsets, baud, amp_end, dev, pipeline=chunks if chunks > 0 else None)
+        elif chunks <= 1:
+            s = RxSession(offsets, baud, amp_end, dev)
+        else:
+            s = PipelinedRxSession(offsets, baud, amp_end, dev, chunks)
         self._cache = (key, s)
         return s
 
-    def close(self):
-        """Releases the cached plan and device buffers."""
+    def _drop_session(self):
+        """Releases the cached plan and device buffers (the pinned wav staging buffer is kept: it only grows)."""
         if getattr(self, "_cache", None) is not None:
             self._cache[1].close()
             self._cache = None
+
+    def close(self):
+        """Releases everything this receiver holds on the device and in pinned host memory."""
+        self._drop_session()
         if getattr(self, "_pinned", None) is not None:
             self._pinned.close()
             self._pinned = None
@@ -503,17 +694,25 @@ class Receiver:
 
     # -- batch API -------------------------------------------------------------------------
     def decode_batch(self, samples, offsets=None, device: int | None = None, baud_rate=None,
-                     amp_end_threshold=None, pipeline: int | None = None) -> RxBatch:
+                     amp_end_threshold=None, pipeline: int | None = None, devices=None) -> RxBatch:
         """Decode B captures.  ``samples``: list of int16 arrays, or one concatenated int16 array
         with ``offsets`` (B+1, in samples).  ``baud_rate`` / ``amp_end_threshold`` (arrays of B) override
         this receiver's settings per capture for mixed corpora.  ``pipeline``: number of capture ranges
         whose upload and decode are overlapped (None: 8 for batches of 64 MB and more, else 1).
-        Raises the reference's exceptions only through ``to_python``; statuses < 0 mark captures on
-        which ``load`` would raise."""
+        ``devices``: several GPUs — the corpus is cut into one contiguous range per device, balanced by
+        predicted time, decoded side by side and gathered into ONE batch in corpus order
+        (ShardedRxSession).  Raises the reference's exceptions only through ``to_python``; statuses < 0
+        mark captures on which ``load`` would raise."""
         if offsets is None:
             samples, offsets = _concat(samples)
-        dev = self._device if device is None else device
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if devices is not None and len(devices) > 1:
+            s = self._session(offsets, tuple(int(d) for d in devices), baud_rate, amp_end_threshold,
+                              chunks=0 if pipeline is None else max(int(pipeline), 1))
+            return s.decode(samples)
+        dev = self._device if device is None else device
+        if devices is not None and len(devices) == 1:
+            dev = int(devices[0])
         if pipeline is None:
             # overlap pays once the copy is much longer than a launch: >= 64 MB of samples, >= 4 captures per range
             big = len(offsets) > 1 and int(offsets[-1]) * 2 >= PIPELINE_MIN_BYTES
@@ -555,19 +754,24 @@ class Receiver:
             return data.decode("utf-8")                                            # :428-429
         return data
 
-    def load_batch(self, filenames, string: bool = True, errors: str = "raise", threads: int = 0, log: bool = True):
+    def load_batch(self, filenames, string: bool = True, errors: str = "raise", threads: int = 0, log: bool = True,
+                   keep_host_copy: bool = False):
         """``load`` over many files in one GPU batch: the library's host threads read the wav files
-        into one pinned buffer while finished spans stream to the GPU, then one decode.
+        through a ring of pinned staging slots while finished spans stream to the GPU, then one decode.
         errors="return" puts the exception object in the list instead of raising at the first
-        failing file."""
+        failing file.  keep_host_copy: read into ONE pinned buffer as large as the corpus instead (kept,
+        grow-only, in this receiver; ``self.last_wav_batch.array`` then holds the frames)."""
         wb = WavBatch(filenames, threads)
         dev = self._device
         s = self._session(wb.offsets, dev)
-        if s.d_samples is None:
-            s.d_samples = DeviceBuffer(dev, (wb.total * 2 + 15) // 16 * 16 + 16)
+        s.ensure_samples()
         s._ext_ptr = None
-        wb.read(getattr(self, "_pinned", None), dev, s.d_samples.ptr)
-        self._pinned = wb.pinned                                 # kept (grow-only) for the next batch
+        if keep_host_copy:
+            wb.read(getattr(self, "_pinned", None), dev, s.d_samples.ptr)
+            self._pinned = wb.pinned                             # kept (grow-only) for the next batch
+            self.last_wav_batch = wb
+        else:
+            wb.read_to_device(dev, s.d_samples)
         s.run()
         batch = s.download()
         out = []
@@ -760,7 +964,8 @@ class TxSession:
         po, pl = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
         _cabi.check(L.afsk_tx_plan_out_offsets(plan, C.byref(po), C.byref(pl)))
         self.out_off = np.ctypeslib.as_array(po, shape=(self.B + 1,)).copy()
-        self.out_len = np.ctypeslib.as_array(pl, shape=(max(self.B, 1),)).copy()[:self.B]
+        # an empty batch has no length array behind the pointer (std::vector::data() of nothing)
+        self.out_len = np.ctypeslib.as_array(pl, shape=(self.B,)).copy() if self.B else np.zeros(0, np.int64)
         self.d_pay = DeviceBuffer(device, len(self.payload))
         self.d_out = DeviceBuffer(device, int(self.out_off[-1]) * 2)
 
@@ -806,7 +1011,10 @@ def write_wav_batch(filenames, samples: np.ndarray, starts, lengths, threads: in
     samples = np.ascontiguousarray(samples, dtype="<i2")
     starts = np.ascontiguousarray(starts, dtype=np.int64)
     lengths = np.ascontiguousarray(lengths, dtype=np.int64)
-    assert len(starts) >= n and len(lengths) >= n
+    if len(starts) < n or len(lengths) < n:
+        raise ValueError("starts and lengths must have one entry per file")
+    if n and (int(starts[:n].min()) < 0 or int(lengths[:n].min()) < 0 or int((starts[:n] + lengths[:n]).max()) > len(samples)):
+        raise ValueError("a file's [start, start + length) range lies outside the sample buffer")
     paths, _keep = _cabi.c_paths(filenames)
     st = np.zeros(max(n, 1), dtype=np.int32)
     _cabi.check(_cabi.lib().afsk_wav_save(paths, n, threads, C.c_void_p(samples.ctypes.data), _cabi.ptr(starts, C.c_int64),

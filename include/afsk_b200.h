@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AFSK_ABI_VERSION 1
+#define AFSK_ABI_VERSION 2
 
 /* return codes */
 #define AFSK_OK 0
@@ -102,7 +102,21 @@ int afsk_rx_plan_create(int device, int B, const int64_t *h_offsets, const int32
  * sample buffer — e.g. the recordings afsk_rx_gate_multi cuts out of a long stream */
 int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const int64_t *h_len,
                                const int32_t *h_baud, const int32_t *h_amp_end, AfskRxPlan **plan);
+/* Re-targets an existing plan at another batch layout (a drop-in Receiver.load sees a different file
+ * length on every call): same arguments as afsk_rx_plan_create_ranges, or h_len == NULL with CSR
+ * h_start[B+1].  The plan's device arena is reused when large enough (it only grows), so the call costs
+ * one host-to-device copy of the descriptors and no allocation.  Output offsets / launch counts queried
+ * earlier are invalidated. */
+int afsk_rx_plan_reset(AfskRxPlan *plan, int B, const int64_t *h_start, const int64_t *h_len,
+                       const int32_t *h_baud, const int32_t *h_amp_end);
 int afsk_rx_plan_destroy(AfskRxPlan *plan);
+/* tuning / test switches of a plan; results never depend on them */
+#define AFSK_OPT_FRAME_KERNEL 1 /* framing kernel: 0 automatic (by capture length), 1 k_frame_warp (one warp per
+                                   capture), 2 k_frame<128,4>, 3 k_frame<512,8>, 4 k_frame<512,8> with 64-bit window
+                                   indices (automatic from 2^30 windows per capture).  A variant that cannot
+                                   represent the batch is replaced by the automatic choice. */
+#define AFSK_OPT_L2_HINT 2      /* L2 evict-first hint on the demodulator's bulk copies: -1 per-kernel default, 0, 1 */
+int afsk_rx_plan_set_option(AfskRxPlan *plan, int option, int value);
 /* capacity offsets (bytes, B+1 entries, host memory owned by the plan) of the decoded output */
 int afsk_rx_plan_out_offsets(const AfskRxPlan *plan, const int64_t **h_out_off);
 /* number of kernel launches one afsk_rx_decode issues for this plan */
@@ -128,10 +142,14 @@ int afsk_rx_plan_planes(const AfskRxPlan *plan, int capture, const uint32_t **d_
 /*
  * Host-buffer convenience (what a drop-in Receiver.load calls): H2D, decode, D2H on `device`.
  * h_out_off[B+1] are capacity offsets into h_out (use afsk_rx_out_capacity per capture).
+ * Calls on one device are serialised; the plan and buffers of the previous call are reused.
  */
 int afsk_rx_decode_host(int device, const int16_t *h_samples, const int64_t *h_offsets, int B,
                         const int32_t *h_baud, const int32_t *h_amp_end, uint8_t *h_out,
                         const int64_t *h_out_off, AfskRxResult *h_res);
+/* afsk_rx_decode_host keeps a plan and grow-only device / pinned buffers per device between calls;
+ * this releases them (also done at process exit by the driver) */
+int afsk_rx_host_release(int device);
 /* upper bound on decoded bytes of a capture of n samples at `baud` */
 int64_t afsk_rx_out_capacity(int64_t n_samples, int baud);
 
@@ -192,7 +210,10 @@ int afsk_wav_probe(const char *const *paths, int n, int threads, int64_t *h_nsam
                    int32_t *h_status);
 /* reads file i's samples into h_dst[h_offsets[i] ...] (pinned memory recommended).  With d_dst != NULL,
  * spans of about span_samples consecutive samples are copied to d_dst (same offsets) on `stream` as
- * soon as their files are in memory, so that reading overlaps the PCIe transfer. */
+ * soon as their files are in memory, so that reading overlaps the PCIe transfer.
+ * h_dst == NULL (d_dst required): the files stream through a process-wide ring of pinned staging slots
+ * (span_samples each, 32 MB by default) straight to the device; no host copy of the corpus is kept, the
+ * first call of a process costs what later calls cost, and the call returns once every copy has landed. */
 int afsk_wav_load(const char *const *paths, int n, int threads, const int64_t *h_data_pos, const int64_t *h_nsamples,
                   const int64_t *h_offsets, int16_t *h_dst, int device, int16_t *d_dst, int64_t span_samples,
                   void *stream, int32_t *h_status);

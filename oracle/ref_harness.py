@@ -181,3 +181,19 @@ def ref_receive_many(stream: np.ndarray, baud: int, amp_start: int, amp_end: int
     finally:
         pa.PyAudio.feed = None
     return calls
+
+
+def load_file_job(job) -> bytes:
+    """(wav path, baud, amp_end) -> what the UNMODIFIED reference's ``Receiver.load(path, False)`` returns
+    (b"" where it raises), with its log silenced (``LOG_LEVEL = 5``) as a user timing it would run it.
+    Picklable for ``multiprocessing.Pool`` — the timing harness of ``bench.py --impl reference --python``."""
+    path, baud, amp_end = job
+    m = module()
+    m.LOG_LEVEL = 5
+    with contextlib.redirect_stdout(io.StringIO()):
+        try:
+            r = m.Receiver(baud, 18000, amp_end)
+            out = r.load(path, False)
+        except Exception:  # noqa: BLE001
+            return b""
+    return out if isinstance(out, bytes) else out.encode("utf-8")

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     L = _cabi.lib()
     for s in declared:
         assert hasattr(L, s), s
-    assert L.afsk_abi_version() == 1
+    assert L.afsk_abi_version() == 2
 
 
 def test_tone_lengths_match_reference_rules():

@@ -54,9 +54,10 @@ struct __align__(16) TileMeta {
     int32_t e0;          // first window's sample offset inside the copy (< 64; the copy starts 16-byte aligned)
     int32_t nwin;        // valid windows in this tile (0 -> nothing to do)
     int32_t thr_bf;      // amp_end * bf : quiet <=> sum|x| < thr_bf
-    int32_t pad;
+    int32_t gpos;        // position of the tile's capture in the group's capture list
     int64_t word_base;   // plane word receiving window 0 of the tile
-    int64_t pad2;
+    uint32_t want;       // consumer-warp arrivals that complete the tile's capture (fused framing)
+    int32_t pad2;
 };
 
 struct DemodParams {
@@ -79,6 +80,20 @@ struct DemodParams {
     int stage_bytes;
     int stages;
     int l2_hint;      // 1: bulk copies carry an L2 evict-first policy
+    // ---- fused mode: auxiliary warps of every CTA recover the clocks and frame the captures of this group
+    //      inside the same launch (k_clock / k_frame_warp become jobs hidden under the HBM stream)
+    int fused;        // 0: clocks come from k_clock (p.clock); 1: from the auxiliary warps (p.cready)
+    int fused_frame;  // 1: the auxiliary warps also run the framing of every capture whose last tile has retired
+    uint32_t epoch;   // decode counter of the plan: a clock word is valid iff its tag equals it
+    int aux_off;      // byte offset of the AuxSmem block in dynamic shared memory
+    uint32_t clk_magic;                  // floor(D / 2bf) == (D * clk_magic) >> clk_shift for D < 2^28
+    int clk_shift;
+    unsigned long long *cready;          // [B] {clock index, epoch tag}: one 64-bit word per capture
+    int32_t *clock_out;                  // [B] clock index as k_clock leaves it (for k_frame / diagnostics)
+    uint32_t *tiles_done;                // [ng] consumer-warp arrivals per capture (reset by the framing job)
+    uint32_t *ctrl;                      // [2][4] job counters {next clock job, next frame job}, slot = epoch & 1
+    uint8_t *out;
+    AfskRxResult *res;
 };
 
 __device__ __forceinline__ long long num_windows(long long n, int bf, int clk)
@@ -246,6 +261,194 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     }
 }
 
+// -------------------------------------------------------------------------- auxiliary warps ----
+// Fused mode.  Every CTA of a demodulator launch carries kAuxWarps extra warps that never touch the sample
+// ring.  Together (all CTAs) they work through two job lists of the launch's capture group, each handed out
+// in capture order by a global counter:
+//   clock jobs  __recoverClockIndex (:322-339) for one capture, by the CTA's auxiliary warps together;
+//               the result is published as one 64-bit word {clock, epoch} that the producer warps poll
+//               before they cut the capture into tiles.  Captures are needed in the same order as the jobs
+//               are handed out, and a claimed job never blocks, so producers cannot starve.
+//   frame jobs  the body of k_frame_warp for one capture, by one auxiliary warp, once every consumer warp of
+//               every tile of the capture has arrived on the capture's counter (release / acquire).
+// The arithmetic is the same as in k_clock / k_frame_warp; only the scheduling differs, so the three-kernel
+// path stays as the reference the tests compare this one with (AFSK_OPT_FUSED).
+constexpr int kAuxWarps = 2;
+constexpr int kAuxThreads = 32 * kAuxWarps;
+constexpr int kFusedThreads = kDemodThreads + kAuxThreads;
+constexpr int kAuxPass = 2048;                 // clock candidates per pass (the prefix array covers one pass)
+constexpr int kAuxMaxVec = 304;                // 16-byte vectors of samples per pass: 2048 + 2 bf + 14 <= 2432
+constexpr int kAuxMaxBf = (kAuxMaxVec * 8 - kAuxPass - 14) / 2;   // 185
+constexpr int kAuxChain = 18;                  // candidates per chain (a quarter bit apart), see k_clock
+constexpr int kAuxRounds = (kAuxMaxVec + kAuxThreads - 1) / kAuxThreads;   // vectors per thread and pass
+constexpr int kAuxQueue = 64;
+
+struct __align__(16) AuxSmem {
+    uint32_t Qs[4 + 8 * kAuxMaxVec];           // Qs[4 + i] = y[0] + ... + y[i], Qs[3] = 0 (as in k_clock)
+    uint32_t warp_tot[kAuxWarps];
+    uint32_t warp_min[kAuxWarps];
+    int job[2];
+    // captures whose last tile retired in THIS CTA, waiting for one of its auxiliary warps (bounded ring;
+    // slot value = capture position + 1, 0 = free)
+    uint32_t q_head, q_tail, done_warps, q_pad;
+    int q_slot[kAuxQueue];
+    uint8_t lut[128];
+};
+
+__device__ __forceinline__ void aux_bar()
+{
+    asm volatile("bar.sync 2, %0;" ::"n"(kAuxThreads) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel_u32(uint32_t *p, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+// plane words written by other CTAs of the same launch: read them from L2 (an L1 line could be stale)
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Clock index of one capture by the kAuxThreads auxiliary threads of a CTA (atid = 0 .. kAuxThreads-1).
+// Same closed form and chains as k_clock; differences: the 4096-frame window is scanned in passes of
+// kAuxPass candidates so that the prefix array is 9.7 KB instead of 16.5 KB (the ring of the short-window
+// kernels leaves no more), and the first minimum is found in ONE sweep as the minimum of the key
+// (floor(D / 2bf) << 12) | i, the floor by a multiply-shift that is exact for D < 2^28.
+__device__ uint32_t aux_clock_index(const int16_t *__restrict__ x, long long off, int bf, uint32_t magic, int shift,
+                                    AuxSmem &S, int atid)
+{
+    const int lane = atid & 31, warp = atid >> 5;
+    const int q = bf >> 2, span = AFSK_SYNC_FRAMES - 2 * bf;    // :327
+    const uint32_t c0 = 65535u * (uint32_t)bf;
+    uint32_t best = 0xFFFFFFFFu;
+    for (int s0 = 0; s0 < span; s0 += kAuxPass) {
+        const int C = min(kAuxPass, span - s0);                 // candidates s0 .. s0 + C - 1
+        const long long g0 = off + s0, ga = g0 & ~7LL;
+        const int e = (int)(g0 - ga);
+        const int nvec = (e + C + 2 * bf + 7) >> 3;             // <= kAuxMaxVec (bf <= kAuxMaxBf, checked on the host)
+        const uint4 *src = reinterpret_cast<const uint4 *>(x + ga);
+        // warp w scans vectors [w * VW, (w + 1) * VW): kAuxRounds rounds of 32 coalesced 16-byte loads
+        constexpr int VW = kAuxRounds * 32;
+        uint32_t carry = 0;
+        uint32_t voff[kAuxRounds];
+#pragma unroll
+        for (int r = 0; r < kAuxRounds; r++) {
+            const int v = warp * VW + r * 32 + lane;
+            uint4 qv = make_uint4(0u, 0u, 0u, 0u);
+            if (v < nvec) qv = ld_nc_v4(src + v);
+            // sum of the vector's 8 samples: IDP.2A with weights (1, 1) adds both halves of a word
+            int run = __dp2a_lo((int)qv.x, 0x0101, 0);
+            run = __dp2a_lo((int)qv.y, 0x0101, run);
+            run = __dp2a_lo((int)qv.z, 0x0101, run);
+            run = __dp2a_lo((int)qv.w, 0x0101, run);
+            uint32_t inc = (uint32_t)run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            voff[r] = carry + inc - (uint32_t)run;
+            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) S.warp_tot[warp] = carry;
+        if (atid == 0) S.Qs[3] = 0;
+        aux_bar();
+        uint32_t base = 0;
+        for (int w = 0; w < warp; w++) base += S.warp_tot[w];
+        // second sweep (the vectors come from L2 again: 4.8 KB per pass): running sums into shared memory
+#pragma unroll
+        for (int r = 0; r < kAuxRounds; r++) {
+            const int v = warp * VW + r * 32 + lane;
+            if (v < nvec) {
+                const uint4 qv = ld_nc_v4(src + v);
+                const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
+                uint32_t run = base + voff[r], pre[8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    run += (uint32_t)(int)(int16_t)(wv[j] & 0xFFFF); pre[2 * j] = run;
+                    run += (uint32_t)(int)(int16_t)(wv[j] >> 16);    pre[2 * j + 1] = run;
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(S.Qs + 4 + v * 8);
+                dst[0] = make_uint4(pre[0], pre[1], pre[2], pre[3]);
+                dst[1] = make_uint4(pre[4], pre[5], pre[6], pre[7]);
+            }
+        }
+        aux_bar();
+        // candidate s0 + il (il < C):  D = c0 + t0 + t8 - 2 (t1 - t2 + t3 - t4 + t6),  t_m = P[il + m q],
+        // P[j] = Qs[3 + e + j].  Item (block b, residue a) is the chain a + q * kAuxChain * b, a + q, ...
+        const uint32_t *Pe = S.Qs + 3 + e;
+        const int qL = q * kAuxChain;
+        const int nitems = ((C + qL - 1) / qL) * q;
+        for (int it = atid; it < nitems; it += kAuxThreads) {
+            const int st = (it % q) + qL * (it / q);
+            int kv = (C - st + q - 1) / q;                       // valid candidates of the chain
+            if (kv <= 0) continue;
+            kv = kv > kAuxChain ? kAuxChain : kv;
+            uint32_t t[9];
+            uint32_t ta = afsk_smem_u32(Pe + st);
+            const uint32_t tstep = 4u * (uint32_t)q;
+#pragma unroll
+            for (int m = 0; m < 8; m++) { t[m] = lds_u32(ta); ta += tstep; }
+            uint32_t idx = (uint32_t)(s0 + st);
+#pragma unroll
+            for (int k = 0; k < kAuxChain; k++) {
+                t[8] = lds_u32_if(ta, k < kv);                  // undefined for k >= kv (never used)
+                ta += tstep;
+                const uint32_t D = c0 + t[0] + t[8] - 2u * (t[1] - t[2] + t[3] - t[4] + t[6]);
+                const uint32_t fl = (uint32_t)(((unsigned long long)D * magic) >> shift);     // getDiff :107
+                const uint32_t key = (fl << 12) | idx;
+                if (k < kv) best = min(best, key);
+                idx += (uint32_t)q;
+#pragma unroll
+                for (int m = 0; m < 8; m++) t[m] = t[m + 1];
+            }
+        }
+        aux_bar();                                               // the next pass overwrites Qs
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+    if (lane == 0) S.warp_min[warp] = best;
+    aux_bar();
+    best = S.warp_min[0];
+#pragma unroll
+    for (int w = 1; w < kAuxWarps; w++) best = min(best, S.warp_min[w]);
+    return best & 4095u;                                         // first index of the minimum (:332-337)
+}
+
+// consumer-side state of fused framing (see signal_step, defined with the framing code below)
+struct TileSignal {
+    int ci = -1;                 // tile finished in the previous iteration, not yet reported
+    uint32_t want = 0;
+    int ci2 = -1;                // reported; the counter value it saw is in old2
+    uint32_t want2 = 0, old2 = 0;
+};
+__device__ __forceinline__ void demod_aux(const DemodParams &p, uint8_t *smem);
+// before the CTA's first barrier: the framing queue starts empty (the auxiliary threads exist only in fused mode)
+__device__ __forceinline__ void aux_smem_init(const DemodParams &p, AuxSmem &S)
+{
+    if (!p.fused) return;
+    const int atid = (int)threadIdx.x - kDemodThreads;
+    if (atid < 0) return;
+    if (atid == 0) { S.q_head = 0u; S.q_tail = 0u; S.done_warps = 0u; }
+    for (int i = atid; i < kAuxQueue; i += kAuxThreads) S.q_slot[i] = 0;
+}
+__device__ __forceinline__ void signal_step(const DemodParams &p, AuxSmem &S, TileSignal &t, int new_ci, uint32_t new_want, int lane);
+__device__ __forceinline__ void signal_finish(const DemodParams &p, AuxSmem &S, TileSignal &t, int lane);
+
 // ------------------------------------------------------------------------------ k_demod ----
 // Per-sample classification (Receiver.__amplify :287-296) and the two getDiff sums (:346-347)
 // in packed integer form.  For a sample x let p = [x > 512], n = [x < -512], c = p - n.
@@ -373,7 +576,15 @@ __device__ __forceinline__ TileJob demod_tile_job(const DemodParams &p, int it, 
     const int4 d0 = *reinterpret_cast<const int4 *>(&p.caps[c].off);          // off, n
     const int4 d1 = *reinterpret_cast<const int4 *>(&p.caps[c].plane_base);   // plane_base, out_off
     const int thr = p.caps[c].thr;
-    const int clk = p.clock[c];
+    int clk;
+    if (p.fused) {
+        // the capture's clock job was handed out before any job of a later capture and never blocks
+        unsigned long long w = ld_relaxed_u64(p.cready + c);
+        while ((uint32_t)(w >> 32) != p.epoch) { __nanosleep(200); w = ld_relaxed_u64(p.cready + c); }
+        clk = (int)(uint32_t)w;
+    } else {
+        clk = p.clock[c];
+    }
     const long long off = ((long long)d0.y << 32) | (unsigned)d0.x, n = ((long long)d0.w << 32) | (unsigned)d0.z;
     const long long plane_base = ((long long)d1.y << 32) | (unsigned)d1.x;
     const long long K = num_windows(n, p.bf, clk);
@@ -388,8 +599,9 @@ __device__ __forceinline__ TileJob demod_tile_job(const DemodParams &p, int it, 
     j.m.e0 = (int)(g0 - ga);
     j.m.nwin = nwin;
     j.m.thr_bf = thr * p.bf;
-    j.m.pad = 0;
+    j.m.gpos = ci;
     j.m.word_base = plane_base + (k0t >> 5);
+    j.m.want = (uint32_t)(kConsumerThreads / 32) * (uint32_t)(p.gtile_first[ci + 1] - first);
     j.m.pad2 = 0;
     j.ga = ga;
     j.bytes = nwin > 0 ? (uint32_t)((((long long)j.m.e0 + (long long)nwin * p.bf) * 2 + 15) & ~15LL) : 0u;
@@ -406,12 +618,17 @@ __device__ __forceinline__ void demod_produce(const DemodParams &p, int ntile, u
     uint32_t ph = 0;                                       // parity of the use count of stage s
     const uint64_t pol = l2_policy_evict_first();
     const bool hint = p.l2_hint != 0;
+    // Tile jobs are resolved a batch ahead of their use, 32 at a time.  In fused mode a job waits for its
+    // capture's clock, and at the start of the launch only one clock job per CTA can be under way: the first
+    // two batches are 8 tiles, so that the stream starts after the first round of clock jobs.
+    int bs = p.fused ? 8 : 32;
     TileJob next = {};
-    if (lane < ntile) next = demod_tile_job(p, first_tile + lane * G, base_mis);
-    for (int base = 0; base < ntile; base += 32) {
+    if (lane < bs && lane < ntile) next = demod_tile_job(p, first_tile + lane * G, base_mis);
+    for (int base = 0; base < ntile;) {
         const TileJob cur = next;
-        if (base + 32 + lane < ntile) next = demod_tile_job(p, first_tile + (base + 32 + lane) * G, base_mis);
-        const int cnt = min(32, ntile - base);
+        const int nbs = (p.fused && base + bs < 16) ? 8 : 32;      // size of the batch after this one
+        if (lane < nbs && base + bs + lane < ntile) next = demod_tile_job(p, first_tile + (base + bs + lane) * G, base_mis);
+        const int cnt = min(bs, ntile - base);
         for (int j = 0; j < cnt; j++) {
             if (lane == j) {
                 if (base + j >= S) {
@@ -431,6 +648,8 @@ __device__ __forceinline__ void demod_produce(const DemodParams &p, int ntile, u
             __syncwarp();
             if (++s == S) { s = 0; ph ^= 1u; }
         }
+        base += bs;
+        bs = nbs;
     }
 }
 
@@ -439,7 +658,7 @@ __device__ __forceinline__ void demod_produce(const DemodParams &p, int ntile, u
 // kMerge: the thread segment is a multiple of 8 samples, so the partial head vector (slots >= e)
 // and the partial tail vector (slots < e) are merged into one full vector with 4 PRMTs.
 template <int kNT, bool kMerge>
-__global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
+__global__ void __launch_bounds__(kFusedThreads, 2) k_demod(const DemodParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -463,7 +682,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     //      selA/selB: PRMT selectors (16 bits each) building the merged vector from head/tail words.
     {
         const int q = p.bf >> 2;
-        for (int idx = tid; idx < wtab_entries; idx += kDemodThreads) {
+        for (int idx = tid; idx < wtab_entries; idx += (int)blockDim.x) {
             const int i = idx % p.nt, e = (idx / p.nt) & 7, part = idx / (p.nt * 8);
             const int seg_lo = part * p.seg, seg_hi = min(p.bf, seg_lo + p.seg);
             uint32_t mk[2] = {0u, 0u}, sp[2] = {0u, 0u}, in[2] = {0u, 0u}, sel[2] = {0u, 0u};
@@ -504,15 +723,22 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
         }
         mbar_fence_init();
     }
+    AuxSmem &AS = *reinterpret_cast<AuxSmem *>(smem + p.aux_off);
+    aux_smem_init(p, AS);
     __syncthreads();
 
     const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
-    if (ntile <= 0) return;
+    if (ntile <= 0) return;                          // never in fused mode: the grid is at most one CTA per tile
 
     if (warp == kConsumerThreads / 32) {
         demod_produce(p, ntile, stage_base, meta, full, empty);
         return;
     }
+    if (warp > kConsumerThreads / 32) {
+        demod_aux(p, smem);
+        return;
+    }
+    TileSignal sig;
 
     // ---------------------------------------------------------------- consumers ----
     const int w = tid >> p.tpw_log2, part = tid & (tpw - 1);
@@ -531,6 +757,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
     for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
+        if (p.fused_frame) signal_step(p, AS, sig, m.gpos, m.want, lane);
         bool bit = false, quiet = false;
         if (m.nwin > 0) {
             const int rel = m.e0 + rel0;
@@ -704,6 +931,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod(const DemodParams p)
         }
         if (++s == S) { s = 0; ph ^= 1u; }
     }
+    if (p.fused_frame) signal_finish(p, AS, sig, lane);
 }
 
 // ------------------------------------------------------------------------ k_demod_shift ----
@@ -772,7 +1000,7 @@ __device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int
 }
 
 template <int kBf, int kWpt>
-__global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodParams p)
+__global__ void __launch_bounds__(kFusedThreads, 2) k_demod_shift(const DemodParams p)
 {
     static_assert(kBf % 4 == 0 && (kBf * kWpt) % 8 == 0 && 32 % kWpt == 0, "segment must be whole vectors");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -791,6 +1019,8 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodPar
         }
         mbar_fence_init();
     }
+    AuxSmem &AS = *reinterpret_cast<AuxSmem *>(smem + p.aux_off);
+    aux_smem_init(p, AS);
     __syncthreads();
 
     const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
@@ -799,6 +1029,11 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodPar
         demod_produce(p, ntile, stage_base, meta, full, empty);
         return;
     }
+    if (warp > kConsumerThreads / 32) {
+        demod_aux(p, smem);
+        return;
+    }
+    TileSignal sig;
 
     const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
     int s = 0;
@@ -806,6 +1041,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodPar
     for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
+        if (p.fused_frame) signal_step(p, AS, sig, m.gpos, m.want, lane);
         uint32_t bits = 0, quiet = 0;
         if (m.nwin > 0) {
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) + tid * (kSeg / 8);
@@ -837,6 +1073,7 @@ __global__ void __launch_bounds__(kDemodThreads, 2) k_demod_shift(const DemodPar
         }
         if (++s == S) { s = 0; ph ^= 1u; }
     }
+    if (p.fused_frame) signal_finish(p, AS, sig, lane);
 }
 
 // ------------------------------------------------------------------------- k_demod_lane ----
@@ -948,9 +1185,10 @@ __device__ __forceinline__ void lane_decode(const uint4 *dp, uint32_t k512, int 
 }
 
 template <int kM, int kJ, int kWarps>
-__global__ void __launch_bounds__(kWarps * 32 + 32, 2) k_demod_lane(const DemodParams p)
+__global__ void __launch_bounds__(kWarps * 32 + 32 + kAuxThreads, 2) k_demod_lane(const DemodParams p)
 {
     static_assert(kJ * 32 * kWarps * 8 * kM * 2 <= 64 * 1024, "tile");
+    static_assert(kWarps * 32 == kConsumerThreads, "the auxiliary warps follow the producer warp");
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.stages;
@@ -966,6 +1204,8 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 2) k_demod_lane(const DemodP
         }
         mbar_fence_init();
     }
+    AuxSmem &AS = *reinterpret_cast<AuxSmem *>(smem + p.aux_off);
+    aux_smem_init(p, AS);
     __syncthreads();
 
     const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
@@ -974,6 +1214,11 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 2) k_demod_lane(const DemodP
         demod_produce(p, ntile, stage_base, meta, full, empty);
         return;
     }
+    if (warp > kWarps) {
+        demod_aux(p, smem);
+        return;
+    }
+    TileSignal sig;
 
     const uint32_t k512 = 0x02000200u | ((uint32_t)p.stages >> 16);
     const int win0 = warp * kJ * 32;                  // first window of this warp in the tile
@@ -982,6 +1227,7 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 2) k_demod_lane(const DemodP
     for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
+        if (p.fused_frame) signal_step(p, AS, sig, m.gpos, m.want, lane);
         uint32_t bw[kJ], qw[kJ];
 #pragma unroll
         for (int j = 0; j < kJ; j++) { bw[j] = 0u; qw[j] = 0u; }
@@ -1015,6 +1261,7 @@ __global__ void __launch_bounds__(kWarps * 32 + 32, 2) k_demod_lane(const DemodP
         }
         if (++s == S) { s = 0; ph ^= 1u; }
     }
+    if (p.fused_frame) signal_finish(p, AS, sig, lane);
 }
 
 // ------------------------------------------------------------------------------ k_frame ----
@@ -1157,25 +1404,22 @@ __global__ void __launch_bounds__(kThreads) k_frame(const CapDesc *__restrict__ 
 constexpr int kFrameWarpCaps = 4;                      // warps (captures) per CTA
 constexpr int64_t kFrameWarpMaxWindows = 262144;       // 8192 plane words: 64 search steps of one warp
 
-__global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDesc *__restrict__ caps,
-                                                                    const int32_t *__restrict__ clock,
-                                                                    const uint2 *__restrict__ planes,
-                                                                    uint8_t *__restrict__ out,
-                                                                    AfskRxResult *__restrict__ res, int B)
+// kCg: the plane words were written by other CTAs of the same launch (fused mode): read them from L2.
+template <bool kCg>
+__device__ __forceinline__ uint32_t plane_word(const uint32_t *p)
 {
-    const int tid = threadIdx.x, lane = tid & 31;
-    __shared__ uint8_t lut[128];
-    static_assert(32 * kFrameWarpCaps == 128, "one LUT entry per thread");
-    lut[tid] = (uint8_t)hamming74_nibble((uint32_t)tid);
-    __syncthreads();
-    const int c = blockIdx.x * kFrameWarpCaps + (tid >> 5);
-    if (c >= B) return;
-    const int clk = clock[c];                          // issued together with the descriptor load
-    const CapDesc d = caps[c];
-    if (d.status0 != 0) return;
+    return kCg ? ld_cg_u32(p) : *p;
+}
+
+// framing of one capture by one warp: the body of k_frame_warp and of the fused kernel's frame jobs
+template <bool kCg>
+__device__ __forceinline__ void frame_capture_warp(int c, const CapDesc &d, int clk, const uint2 *__restrict__ planes,
+                                                   uint8_t *__restrict__ out, AfskRxResult *__restrict__ res,
+                                                   const uint8_t *lut, int lane)
+{
     const int K = (int)num_windows(d.n, d.bf, clk);
     const int nwords = (K + 31) >> 5;
-    const uint2 *PL = planes + d.plane_base;
+    const uint32_t *PW = reinterpret_cast<const uint32_t *>(planes + d.plane_base);   // word j: bits PW[2j], quiet PW[2j + 1]
     constexpr unsigned NONE = 0x7FFFFFFFu;
     constexpr int kWords = 8;                           // plane words per lane per step (loads in flight)
 
@@ -1187,7 +1431,7 @@ __global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDes
         for (int r = kWords - 1; r >= 0; r--) {
             const int j = base + lane + 32 * r;
             if (j < nwords) {
-                const uint32_t cur = PL[j].x, prev = j ? PL[j - 1].x : 0u;
+                const uint32_t cur = plane_word<kCg>(PW + 2 * j), prev = j ? plane_word<kCg>(PW + 2 * j - 2) : 0u;
                 // bit t of M: b[k-3] & ~b[k-2] & ~b[k-1] & ~b[k] for k = 32j + t
                 uint32_t M = __funnelshift_l(prev, cur, 3) & ~__funnelshift_l(prev, cur, 2) &
                              ~__funnelshift_l(prev, cur, 1) & ~cur;
@@ -1208,7 +1452,7 @@ __global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDes
         for (int r = kWords - 1; r >= 0; r--) {
             const int j = base + lane + 32 * r;
             if (j < nwords) {
-                uint32_t M = PL[j].y;
+                uint32_t M = plane_word<kCg>(PW + 2 * j + 1);
                 if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
                 const int rem = K - 32 * j;
                 if (rem < 32) M &= (1u << rem) - 1u;
@@ -1229,7 +1473,7 @@ __global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDes
         const int pos = k0 + 56 * i;
         const int wi = pos >> 5;
         const uint32_t sh = (uint32_t)(pos & 31);
-        const uint32_t w0 = PL[wi].x, w1 = PL[wi + 1].x, w2 = PL[wi + 2].x;
+        const uint32_t w0 = plane_word<kCg>(PW + 2 * wi), w1 = plane_word<kCg>(PW + 2 * wi + 2), w2 = plane_word<kCg>(PW + 2 * wi + 4);
         uint32_t word = 0;
 #pragma unroll
         for (int jb = 0; jb < 4; jb++) {
@@ -1242,7 +1486,7 @@ __global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDes
     }
     for (int i = 4 * nquad + lane; i < nbytes; i += 32) {
         const int pos = k0 + 14 * i;
-        const uint32_t lo = PL[pos >> 5].x, hi = PL[(pos >> 5) + 1].x;
+        const uint32_t lo = plane_word<kCg>(PW + 2 * (pos >> 5)), hi = plane_word<kCg>(PW + 2 * (pos >> 5) + 2);
         o[i] = (uint8_t)decode_byte(__funnelshift_r(lo, hi, (uint32_t)(pos & 31)) & 0x3FFFu, lut);
     }
     if (lane == 0) {
@@ -1254,6 +1498,134 @@ __global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDes
         r.nbytes = nbits > 0 ? nbytes : 0;
         res[c] = r;
     }
+}
+
+__global__ void __launch_bounds__(32 * kFrameWarpCaps) k_frame_warp(const CapDesc *__restrict__ caps,
+                                                                    const int32_t *__restrict__ clock,
+                                                                    const uint2 *__restrict__ planes,
+                                                                    uint8_t *__restrict__ out,
+                                                                    AfskRxResult *__restrict__ res, int B)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ uint8_t lut[128];
+    static_assert(32 * kFrameWarpCaps == 128, "one LUT entry per thread");
+    lut[tid] = (uint8_t)hamming74_nibble((uint32_t)tid);
+    __syncthreads();
+    const int c = blockIdx.x * kFrameWarpCaps + (tid >> 5);
+    if (c >= B) return;
+    const int clk = clock[c];                          // issued together with the descriptor load
+    const CapDesc d = caps[c];
+    if (d.status0 != 0) return;
+    frame_capture_warp<false>(c, d, clk, planes, out, res, lut, lane);
+}
+
+// results of the captures that are decided on the host (exceptions, too short): the fused path has no k_clock
+__global__ void __launch_bounds__(256) k_preset(const CapDesc *__restrict__ caps, int32_t *__restrict__ clock,
+                                                AfskRxResult *__restrict__ res, int B)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    const int st = caps[c].status0;
+    if (st == 0) return;
+    clock[c] = -1;
+    AfskRxResult r;
+    r.status = st; r.clock = -1; r.train_end = -1; r.nbits = 0; r.nbytes = 0;
+    res[c] = r;
+}
+
+// The auxiliary warps of one CTA of a fused demodulator launch (see "auxiliary warps" above).
+__device__ __forceinline__ bool aux_pop_and_frame(const DemodParams &p, AuxSmem &S, int lane)
+{
+    // claims one queued capture (if any) for this warp and frames it
+    int v = 0;
+    if (lane == 0) {
+        while (true) {
+            const uint32_t h = *reinterpret_cast<volatile uint32_t *>(&S.q_head);
+            if (h == *reinterpret_cast<volatile uint32_t *>(&S.q_tail)) break;
+            if (atomicCAS(&S.q_head, h, h + 1u) != h) continue;
+            // the pusher took its ticket before it wrote the slot
+            while ((v = atomicExch(&S.q_slot[h % kAuxQueue], 0)) == 0) __nanosleep(64);
+            break;
+        }
+        __threadfence_block();                        // acquire: the pusher's acquire of the capture's tiles
+    }
+    v = __shfl_sync(0xFFFFFFFFu, v, 0);
+    if (v == 0) return false;
+    const int c = p.gcaps[v - 1];
+    const CapDesc d = p.caps[c];
+    const int clk = (int)(uint32_t)ld_relaxed_u64(p.cready + c);
+    frame_capture_warp<true>(c, d, clk, p.planes, p.out, p.res, S.lut, lane);
+    return true;
+}
+
+__device__ __forceinline__ void demod_aux(const DemodParams &p, uint8_t *smem)
+{
+    AuxSmem &S = *reinterpret_cast<AuxSmem *>(smem + p.aux_off);
+    const int atid = (int)threadIdx.x - kDemodThreads, lane = atid & 31;
+    uint32_t *ctrl = p.ctrl + 4 * (p.epoch & 1u);
+    if (blockIdx.x == 0 && atid == 0) {               // the other slot serves the next launch of this group
+        uint32_t *other = p.ctrl + 4 * ((p.epoch + 1u) & 1u);
+        other[0] = 0u; other[1] = 0u;
+    }
+    // ---- clock jobs, in capture order, the auxiliary warps of the CTA together; between two clock jobs
+    //      every warp frames at most one capture that has retired in this CTA meanwhile ----
+    for (int it = 0;; it++) {
+        if (atid == 0) S.job[it & 1] = (int)atomicAdd(&ctrl[0], 1u);
+        aux_bar();
+        const int j = S.job[it & 1];
+        if (j >= p.ng) break;
+        const int c = p.gcaps[j];
+        const long long off = p.caps[c].off;
+        const uint32_t clk = aux_clock_index(p.samples, off, p.bf, p.clk_magic, p.clk_shift, S, atid);
+        if (atid == 0) {
+            p.clock_out[c] = (int32_t)clk;
+            st_relaxed_u64(p.cready + c, ((unsigned long long)p.epoch << 32) | clk);
+        }
+        if (p.fused_frame) aux_pop_and_frame(p, S, lane);
+    }
+    if (!p.fused_frame) return;
+    // ---- the rest of the CTA's captures, until its consumer warps are gone and the queue is empty ----
+    while (true) {
+        if (aux_pop_and_frame(p, S, lane)) continue;
+        const uint32_t done = *reinterpret_cast<volatile uint32_t *>(&S.done_warps);
+        if (done == (uint32_t)(kConsumerThreads / 32) &&
+            *reinterpret_cast<volatile uint32_t *>(&S.q_head) == *reinterpret_cast<volatile uint32_t *>(&S.q_tail))
+            break;
+        __nanosleep(200);
+    }
+}
+
+// Consumer side of fused framing.  A consumer warp reports a finished tile to the tile's capture one
+// iteration late (its plane stores have long landed by then, so the release costs no wait) and reads the
+// answer of that report another iteration later (so the atomic's round trip is never waited for either).
+// The warp whose arrival completes a capture queues it for the CTA's auxiliary warps.
+__device__ __forceinline__ void aux_push(AuxSmem &S, int ci)
+{
+    __threadfence_block();                            // release: what this thread acquired goes with the slot
+    const uint32_t t = atomicAdd(&S.q_tail, 1u);
+    while (atomicCAS(&S.q_slot[t % kAuxQueue], 0, ci + 1) != 0) __nanosleep(64);   // ring full: the CTA's auxiliary warps drain it
+}
+
+__device__ __forceinline__ void signal_step(const DemodParams &p, AuxSmem &S, TileSignal &t, int new_ci, uint32_t new_want, int lane)
+{
+    __syncwarp();                                     // the other lanes' plane stores of the previous tile
+    if (lane == 0) {
+        if (t.ci2 >= 0 && t.old2 + 1u == t.want2) {
+            p.tiles_done[t.ci2] = 0u;                 // last arrival: nobody touches the counter again in this launch
+            aux_push(S, t.ci2);
+        }
+        t.ci2 = t.ci; t.want2 = t.want;
+        if (t.ci >= 0) t.old2 = atom_add_acq_rel_u32(p.tiles_done + t.ci, 1u);
+        t.ci = new_ci; t.want = new_want;
+    }
+}
+
+// after a consumer warp's last tile
+__device__ __forceinline__ void signal_finish(const DemodParams &p, AuxSmem &S, TileSignal &t, int lane)
+{
+    signal_step(p, S, t, -1, 0u, lane);
+    signal_step(p, S, t, -1, 0u, lane);
+    if (lane == 0) atomicAdd(&S.done_warps, 1u);
 }
 
 // ------------------------------------------------------------------------------- k_gate ----
@@ -1399,8 +1771,16 @@ struct Group {
     int shift_wpt = 0;            // > 0: k_demod_shift<bf, shift_wpt>
     size_t smem = 0;
     int grid = 0;
+    // fused mode (auxiliary warps): shared memory with the AuxSmem block appended, its offset, the grid for
+    // that footprint, the exact multiply-shift for floor(D / 2bf), per-capture arrival counters and job counters
+    size_t smem_fused = 0;
+    int aux_off = 0, grid_fused = 0;
+    bool can_fuse = false;
+    uint32_t clk_magic = 0;
+    int clk_shift = 0;
     std::vector<int32_t> caps, tile_first, tile_gpos;
     int32_t *d_caps = nullptr, *d_tile_first = nullptr, *d_tile_gpos = nullptr;   // inside the plan's arena
+    uint32_t *d_tiles_done = nullptr, *d_ctrl = nullptr;
 };
 
 }  // namespace
@@ -1424,15 +1804,15 @@ static cudaError_t demod_set_smem_attr()
     return e;
 }
 
-static void launch_demod(int merge, int nt, int grid, size_t smem, cudaStream_t st, const DemodParams &p)
+static void launch_demod(int merge, int nt, int grid, int block, size_t smem, cudaStream_t st, const DemodParams &p)
 {
 #define X(NT, MG) \
-    if ((MG) == (merge != 0) && (NT) == nt) { k_demod<NT, MG><<<grid, kDemodThreads, smem, st>>>(p); return; }
+    if ((MG) == (merge != 0) && (NT) == nt) { k_demod<NT, MG><<<grid, block, smem, st>>>(p); return; }
     AFSK_DEMOD_VARIANTS(X)
 #undef X
     DemodParams q = p;          // no specialised variant: generic loop over nv vectors
     q.merge = 0;
-    k_demod<0, false><<<grid, kDemodThreads, smem, st>>>(q);
+    k_demod<0, false><<<grid, block, smem, st>>>(q);
 }
 
 struct AfskRxPlan {
@@ -1454,6 +1834,12 @@ struct AfskRxPlan {
     int64_t max_windows = 0;
     int64_t sum_windows = 0;      // over the captures decoded on the GPU
     int64_t gpu_caps = 0;
+    unsigned long long *d_cready = nullptr;   // fused mode: {clock, epoch tag} per capture
+    uint32_t epoch = 0;           // decodes issued with this plan (fused mode tags)
+    int n_preset = 0;             // captures whose result is decided on the host (status0 != 0)
+    int64_t sum_samples = 0;      // over the captures decoded on the GPU
+    bool can_fuse = false;        // every group fits the auxiliary warps (bit length, shared memory)
+    int fused = -1;               // AFSK_OPT_FUSED: -1 automatic, 0 three kernels, 1 fused whenever possible
     int frame_kernel = 0;         // AFSK_OPT_FRAME_KERNEL: 0 automatic, 1 k_frame_warp, 2 k_frame<128,4,int>, 3 <512,8,int>, 4 <512,8,long long>
     int l2_hint = -1;             // AFSK_OPT_L2_HINT / AFSK_L2_HINT (read once per plan): -1 per-kernel default
     bool timing = false;
@@ -1588,7 +1974,8 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
     P->caps.assign((size_t)B, CapDesc());
     P->out_off.assign((size_t)B + 1, 0);
     P->groups.clear();
-    P->max_windows = P->sum_windows = P->gpu_caps = 0;
+    P->max_windows = P->sum_windows = P->gpu_caps = P->sum_samples = 0;
+    P->n_preset = 0;
     std::map<int, int> bf_to_group;
     int64_t words = 0;
     for (int c = 0; c < B; c++) {
@@ -1627,6 +2014,7 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
             const int64_t ntiles = (kmax + g.wt - 1) / g.wt;
             P->max_windows = std::max(P->max_windows, kmax);
             P->sum_windows += kmax;
+            P->sum_samples += d.n;
             P->gpu_caps++;
             if (ntiles + (int64_t)g.tile_first.back() > 0x7FFFFFF0LL) { afsk_set_error("batch too large"); return AFSK_E_ARG; }
             g.caps.push_back(c);
@@ -1634,6 +2022,8 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
             g.tile_first.push_back(g.tile_first.back() + (int32_t)ntiles);
             words += ntiles * (g.wt / 32) + 4;
             cap_bytes = (kmax / 14 + 16 + 15) & ~(int64_t)15;
+        } else {
+            P->n_preset++;
         }
         P->out_off[c + 1] = P->out_off[c] + cap_bytes;
     }
@@ -1647,18 +2037,21 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
         goff.push_back(desc_bytes); desc_bytes += align16(sizeof(int32_t) * g.caps.size());
         goff.push_back(desc_bytes); desc_bytes += align16(sizeof(int32_t) * g.tile_first.size());
         goff.push_back(desc_bytes); desc_bytes += align16(sizeof(int32_t) * g.tile_gpos.size());
+        goff.push_back(desc_bytes); desc_bytes += align16(sizeof(uint32_t) * g.caps.size());    // tiles_done: zeros
+        goff.push_back(desc_bytes); desc_bytes += align16(sizeof(uint32_t) * 8);                // ctrl[2][4]: zeros
     }
     desc_bytes = (desc_bytes + 255) & ~(size_t)255;
     const size_t clock_off = desc_bytes;
-    const size_t planes_off = clock_off + ((sizeof(int32_t) * (size_t)(B ? B : 1) + 255) & ~(size_t)255);
+    const size_t cready_off = clock_off + ((sizeof(int32_t) * (size_t)(B ? B : 1) + 255) & ~(size_t)255);
+    const size_t planes_off = cready_off + ((sizeof(unsigned long long) * (size_t)(B ? B : 1) + 255) & ~(size_t)255);
     const size_t need = planes_off + sizeof(uint2) * (size_t)P->plane_words;
     P->h_desc.assign(desc_bytes, 0);
     if (B) memcpy(P->h_desc.data(), P->caps.data(), sizeof(CapDesc) * (size_t)B);
     for (size_t gi = 0; gi < P->groups.size(); gi++) {
         Group &g = P->groups[gi];
-        memcpy(P->h_desc.data() + goff[3 * gi], g.caps.data(), sizeof(int32_t) * g.caps.size());
-        memcpy(P->h_desc.data() + goff[3 * gi + 1], g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());
-        memcpy(P->h_desc.data() + goff[3 * gi + 2], g.tile_gpos.data(), sizeof(int32_t) * g.tile_gpos.size());
+        memcpy(P->h_desc.data() + goff[5 * gi], g.caps.data(), sizeof(int32_t) * g.caps.size());
+        memcpy(P->h_desc.data() + goff[5 * gi + 1], g.tile_first.data(), sizeof(int32_t) * g.tile_first.size());
+        memcpy(P->h_desc.data() + goff[5 * gi + 2], g.tile_gpos.data(), sizeof(int32_t) * g.tile_gpos.size());
         g.tile_gpos.clear(); g.tile_gpos.shrink_to_fit();
     }
     cudaError_t e = cudaSuccess;
@@ -1680,17 +2073,35 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
     if (e == cudaSuccess) {
         P->d_caps = reinterpret_cast<CapDesc *>(P->arena);
         P->d_clock = reinterpret_cast<int32_t *>(P->arena + clock_off);
+        P->d_cready = reinterpret_cast<unsigned long long *>(P->arena + cready_off);
         P->d_planes = reinterpret_cast<uint2 *>(P->arena + planes_off);
+        P->can_fuse = !P->groups.empty();
         for (size_t gi = 0; gi < P->groups.size(); gi++) {
             Group &g = P->groups[gi];
-            g.d_caps = reinterpret_cast<int32_t *>(P->arena + goff[3 * gi]);
-            g.d_tile_first = reinterpret_cast<int32_t *>(P->arena + goff[3 * gi + 1]);
-            g.d_tile_gpos = reinterpret_cast<int32_t *>(P->arena + goff[3 * gi + 2]);
+            g.d_caps = reinterpret_cast<int32_t *>(P->arena + goff[5 * gi]);
+            g.d_tile_first = reinterpret_cast<int32_t *>(P->arena + goff[5 * gi + 1]);
+            g.d_tile_gpos = reinterpret_cast<int32_t *>(P->arena + goff[5 * gi + 2]);
+            g.d_tiles_done = reinterpret_cast<uint32_t *>(P->arena + goff[5 * gi + 3]);
+            g.d_ctrl = reinterpret_cast<uint32_t *>(P->arena + goff[5 * gi + 4]);
             const int total = g.tile_first.back();
             // two CTAs per SM even where three would fit: measured on one box, 3 CTAs per SM give 6223 GB/s
             // against 7115 at 1200 baud and 5663 against 6610 at 300 baud (profiles/r1_tuning_log.md)
             const int per_sm = g.smem <= 113 * 1024 ? 2 : 1;
             g.grid = std::max(1, std::min(total, P->sm_count * per_sm));
+            // fused mode: the AuxSmem block behind everything else; the CTAs per SM must not drop
+            g.aux_off = (int)((g.smem + 15) & ~(size_t)15);
+            g.smem_fused = (size_t)g.aux_off + sizeof(AuxSmem);
+            const int per_sm_f = g.smem_fused <= 113 * 1024 ? 2 : 1;
+            g.can_fuse = g.bf <= kAuxMaxBf && g.smem_fused <= 227 * 1024 && per_sm_f == per_sm;
+            g.grid_fused = std::max(1, std::min(total, P->sm_count * per_sm_f));
+            // floor(D / d) == (D * magic) >> shift for every D < 2^28, d = 2 bf (Granlund-Montgomery: l = ceil(log2 d),
+            // magic = ceil(2^(28 + l) / d) < 2^29)
+            const uint32_t dv = 2u * (uint32_t)g.bf;
+            int l = 0;
+            while ((1u << l) < dv) l++;
+            g.clk_shift = 28 + l;
+            g.clk_magic = (uint32_t)((((unsigned long long)1 << g.clk_shift) + dv - 1) / dv);
+            if (!g.can_fuse) P->can_fuse = false;
         }
         static bool attr_set[64] = {};
         if (P->device < 0 || P->device >= 64 || !attr_set[P->device]) {
@@ -1739,8 +2150,10 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     P->device = device;
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) P->sm_count = sms;
-    const char *ev = getenv("AFSK_L2_HINT");            // tuning override, read once per plan
+    const char *ev = getenv("AFSK_L2_HINT");            // tuning overrides, read once per plan
     if (ev) P->l2_hint = atoi(ev);
+    ev = getenv("AFSK_FUSED");
+    if (ev) P->fused = atoi(ev) < 0 ? -1 : (atoi(ev) ? 1 : 0);
     const int rc = plan_build(P, B, h_start, h_len, h_baud, h_amp_end);
     if (rc != AFSK_OK) { afsk_rx_plan_destroy(P); return rc; }
     *plan_out = P;
@@ -1790,6 +2203,9 @@ int afsk_rx_plan_set_option(AfskRxPlan *P, int option, int value)
     case AFSK_OPT_L2_HINT:
         P->l2_hint = value < 0 ? -1 : (value ? 1 : 0);
         return AFSK_OK;
+    case AFSK_OPT_FUSED:
+        P->fused = value < 0 ? -1 : (value ? 1 : 0);
+        return AFSK_OK;
     default:
         afsk_set_error("afsk_rx_plan_set_option: unknown option %d", option);
         return AFSK_E_ARG;
@@ -1803,10 +2219,26 @@ int afsk_rx_plan_out_offsets(const AfskRxPlan *P, const int64_t **h_out_off)
     return AFSK_OK;
 }
 
+// which of the two schedules a decode of this plan uses (see "auxiliary warps")
+static bool plan_fused(const AfskRxPlan *P)
+{
+    if (!P->can_fuse || P->fused == 0) return false;
+    if (P->fused == 1) return true;
+    // automatic: the auxiliary warps of the whole grid retire about 45 captures per microsecond (clock + framing),
+    // the stream 3.3 G samples per millisecond: captures must average 73 K samples for the jobs to hide under it
+    return P->sum_samples >= (int64_t)98304 * std::max<int64_t>(P->gpu_caps, 1);
+}
+static bool plan_fused_frame(const AfskRxPlan *P)
+{
+    return plan_fused(P) && P->max_windows <= kFrameWarpMaxWindows && P->frame_kernel <= 1;
+}
+
 int afsk_rx_plan_launches(const AfskRxPlan *P, int *launches)
 {
     if (!P || !launches) return AFSK_E_ARG;
-    *launches = P->B > 0 ? 2 + (int)P->groups.size() : 0;
+    if (P->B == 0) *launches = 0;
+    else if (plan_fused(P)) *launches = (int)P->groups.size() + (P->n_preset > 0 ? 1 : 0) + (plan_fused_frame(P) ? 0 : 1);
+    else *launches = 2 + (int)P->groups.size();
     return AFSK_OK;
 }
 
@@ -1856,7 +2288,14 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     AfskDeviceGuard guard(P->device);
     if (!guard.ok) { afsk_set_error("cannot select device %d", P->device); return AFSK_E_CUDA; }
     cudaStream_t st = (cudaStream_t)stream;
-    k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
+    const bool fused = plan_fused(P), fused_frame = plan_fused_frame(P);
+    if (fused) {
+        P->epoch++;
+        if (P->epoch == 0) P->epoch = 1;                 // tag 0 is what a fresh arena holds
+        if (P->n_preset > 0) k_preset<<<(P->B + 255) / 256, 256, 0, st>>>(P->d_caps, P->d_clock, d_res, P->B);
+    } else {
+        k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
+    }
     for (const Group &g : P->groups) {
         DemodParams p;
         p.samples = d_samples; p.caps = P->d_caps; p.clock = P->d_clock;
@@ -1870,19 +2309,30 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 (environment, read at
         // plan creation) or AFSK_OPT_L2_HINT force it.
         p.l2_hint = P->l2_hint >= 0 ? P->l2_hint : (g.small_wpt ? 0 : 1);
+        p.fused = fused ? 1 : 0; p.fused_frame = fused_frame ? 1 : 0;
+        p.epoch = P->epoch; p.aux_off = g.aux_off; p.clk_magic = g.clk_magic; p.clk_shift = g.clk_shift;
+        p.cready = P->d_cready; p.clock_out = P->d_clock; p.tiles_done = g.d_tiles_done; p.ctrl = g.d_ctrl;
+        p.out = d_out; p.res = d_res;
+        const int grid = fused ? g.grid_fused : g.grid;
+        const int block = fused ? kFusedThreads : kDemodThreads;
+        const size_t smem = fused ? g.smem_fused : g.smem;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
             cudaEventRecord(e0, st);
-        if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2, 8><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<g.grid, kDemodThreads, g.smem, st>>>(p);
-        else launch_demod(g.merge, g.nt, g.grid, g.smem, st, p);
+        if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8, 8><<<grid, block, smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4, 8><<<grid, block, smem, st>>>(p);
+        else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2, 8><<<grid, block, smem, st>>>(p);
+        else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<grid, block, smem, st>>>(p);
+        else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<grid, block, smem, st>>>(p);
+        else launch_demod(g.merge, g.nt, grid, block, smem, st, p);
         if (e0 && e1) {
             cudaEventRecord(e1, st);
             P->timing_events.emplace_back(e0, e1);
         }
+    }
+    if (fused_frame) {
+        AFSK_CUDA(cudaGetLastError());
+        return AFSK_OK;
     }
     // framing kernel: automatic by capture length, or forced (AFSK_OPT_FRAME_KERNEL) where the forced variant can
     // represent the batch (k_frame_warp: <= 2^18 windows per capture; int indices: < 2^30)

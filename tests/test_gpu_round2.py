@@ -268,3 +268,114 @@ def test_empty_tx_batch(tmp_path):
     # one empty payload is still a full frame: training + terminator + tail
     one = t.encode_batch([b""])
     assert np.array_equal(one.frames(0), O.tx_frames(b"", 1200))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused schedule: clock recovery and framing as jobs of auxiliary warps inside the streaming kernel
+def _decode_with(samples, offsets, baud, thr, fused, frame_kernel=0, repeats=1):
+    s = A.RxSession(offsets, baud, thr)
+    L = _cabi.lib()
+    _cabi.check(L.afsk_rx_plan_set_option(s.plan, _cabi.OPT_FUSED, fused))
+    _cabi.check(L.afsk_rx_plan_set_option(s.plan, _cabi.OPT_FRAME_KERNEL, frame_kernel))
+    n = C.c_int(0)
+    _cabi.check(L.afsk_rx_plan_launches(s.plan, C.byref(n)))
+    s.upload(samples)
+    out = None
+    for _ in range(repeats):
+        s.run()
+        b = s.download()
+        if out is not None:
+            assert np.array_equal(out.results, b.results) and out.payloads() == b.payloads(), "repeat decode differs"
+        out = b
+    s.close()
+    return out, n.value
+
+
+def test_fused_equals_three_kernels_and_oracle_mixed():
+    caps, baud, thr, _ = _mixed_corpus(51, 160, bauds=(300, 600, 1200, 2400, 4000, 6000, 4800, 9600, 1500, 800, 2000, 3000, 375))
+    samples, offsets = A.modem._concat(caps)
+    three, n3 = _decode_with(samples, offsets, baud, thr, 0)
+    fused, nf = _decode_with(samples, offsets, baud, thr, 1, repeats=4)
+    assert nf < n3, (nf, n3)                      # one launch per bit length (+ the preset kernel), no k_clock / k_frame
+    assert np.array_equal(three.results, fused.results)
+    assert three.payloads() == fused.payloads()
+    _assert_equals_oracle(fused, caps, baud, thr)
+    # fused clocks with a separate framing kernel
+    half, nh = _decode_with(samples, offsets, baud, thr, 1, frame_kernel=2)
+    assert nh == nf + 1
+    assert np.array_equal(three.results, half.results) and three.payloads() == half.payloads()
+
+
+def test_fused_many_short_captures_and_every_start_alignment():
+    """Thousands of captures of one or two tiles each: every CTA completes far more captures than its
+    framing queue holds while its auxiliary warps are still busy with clock jobs; every 16-byte phase of the
+    capture start; captures just above the 4096-frame minimum; a too-short and an empty one in between."""
+    rng = np.random.default_rng(52)
+    base = [O.tx_frames(rng.integers(0, 256, n, dtype=np.uint8).tobytes(), 6000, 0.02) for n in (1, 5, 16, 40)]
+    caps = []
+    for i in range(6000):
+        fr = base[i % 4]
+        x = np.concatenate([np.zeros(i % 23, np.int16), fr]).astype(np.int32)
+        if i % 3:
+            x = x + np.round(rng.normal(0, 5000, len(x))).astype(np.int32)
+        caps.append(np.clip(x, -32768, 32767).astype(np.int16))
+    caps[100] = caps[100][:3000]
+    caps[200] = np.zeros(0, np.int16)
+    baud = np.full(len(caps), 6000, np.int32)
+    thr = np.full(len(caps), 14000, np.int32)
+    samples, offsets = A.modem._concat(caps)
+    three, _ = _decode_with(samples, offsets, baud, thr, 0)
+    fused, _ = _decode_with(samples, offsets, baud, thr, 1, repeats=3)
+    assert np.array_equal(three.results, fused.results) and three.payloads() == fused.payloads()
+    for i in list(range(0, 6000, 97)) + [100, 200]:
+        o = O.rx_decode(caps[i], 6000, 14000)
+        assert (int(fused.status[i]), int(fused.clock[i]), int(fused.nbits[i]), fused.payload(i)) == \
+               (o["status"], o["clock"], o["nbits"], o["data"]), i
+
+
+@pytest.mark.parametrize("baud", [6000, 3000, 2000, 4000, 2400, 1200, 600, 300, 1500, 750, 375, 800, 480, 400, 1000, 500, 12000])
+def test_fused_clock_every_baud_and_offset(baud):
+    """The auxiliary warps' clock search (two passes of 2048 candidates, multiply-shift floor, key minimum) against
+    the oracle's first minimum: every capture start phase, clock offsets over a whole training cycle, clean and
+    noisy, plus noise-only captures where the minimum is anywhere in the window."""
+    rng = np.random.default_rng([53, baud])
+    bf = 48000 // baud
+    caps = []
+    for i in range(2 * bf + 9):
+        fr = O.tx_frames(b"clock", baud, 0.25)
+        lead = i if i < 2 * bf else int(rng.integers(0, 4000))
+        x = np.concatenate([np.zeros(lead, np.int16), fr]).astype(np.int32)
+        if i % 2:
+            x = x + np.round(rng.normal(0, float(rng.choice([3000, 12000, 30000])), len(x))).astype(np.int32)
+        caps.append(np.clip(x, -32768, 32767).astype(np.int16))
+    for i in range(24):
+        caps.append(np.clip(np.round(rng.normal(0, 9000, 4096 + 37 * i)), -32768, 32767).astype(np.int16))
+    b = np.full(len(caps), baud, np.int32)
+    thr = np.full(len(caps), 14000, np.int32)
+    samples, offsets = A.modem._concat(caps)
+    fused, _ = _decode_with(samples, offsets, b, thr, 1)
+    _assert_equals_oracle(fused, caps, b, thr)
+
+
+def test_fused_long_capture_and_retargeted_plan():
+    """A capture of more than 2^18 bit windows keeps the separate framing kernel (fused clocks only); the same
+    plan is then re-targeted at short captures (fused framing) and back."""
+    rng = np.random.default_rng(54)
+    pl = rng.integers(0, 256, 40000, dtype=np.uint8).tobytes()
+    long_cap = O.tx_frames(pl, 6000, 0.1)                     # 560 K windows of 8 frames
+    long_cap = np.clip(long_cap.astype(np.int32) + np.round(rng.normal(0, 6000, len(long_cap))).astype(np.int32), -32768, 32767).astype(np.int16)
+    shorts, baud, thr, _ = _mixed_corpus(55, 30, bauds=(6000, 1200))
+    rx = A.Receiver(6000)
+    os.environ["AFSK_FUSED"] = "1"
+    try:
+        for caps, bd, th in (([long_cap], np.array([6000], np.int32), np.array([14000], np.int32)), (shorts, baud, thr),
+                             ([long_cap, shorts[0]], np.array([6000, baud[0]], np.int32), np.array([14000, thr[0]], np.int32)),
+                             (shorts[:3], baud[:3], thr[:3])):
+            b = rx.decode_batch(caps, baud_rate=bd, amp_end_threshold=th)
+            _cabi.check(_cabi.lib().afsk_rx_plan_set_option(rx._cache[1].plan, _cabi.OPT_FUSED, 1))
+            b2 = rx.decode_batch(caps, baud_rate=bd, amp_end_threshold=th)
+            assert np.array_equal(b.results, b2.results) and b.payloads() == b2.payloads()
+            _assert_equals_oracle(b2, caps, bd, th)
+    finally:
+        os.environ.pop("AFSK_FUSED")
+        rx.close()

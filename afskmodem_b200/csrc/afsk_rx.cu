@@ -30,6 +30,33 @@
 
 #include "afsk_common.cuh"
 
+#ifdef AFSK_DBG_TRACE
+// debugging build only: time stamps (ns, %globaltimer) of auxiliary-warp jobs, read back by afsk_dbg_trace_read
+__device__ unsigned long long g_trace[1 << 16];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ unsigned long long trace_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define AFSK_TRACE_DECL unsigned long long tr__[8]; int trn__ = 0;
+#define AFSK_TRACE_MARK if (trn__ < 8) tr__[trn__++] = trace_now();
+#define AFSK_TRACE_EMIT(kind)                                                              \
+    if ((threadIdx.x & 31) == 0 && ((kind) != 1ull || (blockIdx.x & 15) == 0)) {           \
+        const unsigned int slot__ = atomicAdd(&g_trace_n, 1u);                             \
+        if (slot__ < (1u << 12)) {                                                         \
+            g_trace[slot__ * 10] = (kind);                                                 \
+            g_trace[slot__ * 10 + 1] = (unsigned long long)trn__;                          \
+            for (int q__ = 0; q__ < 8; q__++) g_trace[slot__ * 10 + 2 + q__] = q__ < trn__ ? tr__[q__] : 0ull; \
+        }                                                                                  \
+    }
+#else
+#define AFSK_TRACE_DECL
+#define AFSK_TRACE_MARK
+#define AFSK_TRACE_EMIT(kind)
+#endif
+
 namespace {
 
 constexpr int kConsumerThreads = 256;
@@ -56,7 +83,7 @@ struct __align__(16) TileMeta {
     int32_t thr_bf;      // amp_end * bf : quiet <=> sum|x| < thr_bf
     int32_t gpos;        // position of the tile's capture in the group's capture list
     int64_t word_base;   // plane word receiving window 0 of the tile
-    uint32_t want;       // consumer-warp arrivals that complete the tile's capture (fused framing)
+    uint32_t want;       // tiles of the tile's capture (fused framing: the capture is complete when all have been reported)
     int32_t pad2;
 };
 
@@ -91,7 +118,7 @@ struct DemodParams {
     unsigned long long *cready;          // [B] {clock index, epoch tag}: one 64-bit word per capture
     int32_t *clock_out;                  // [B] clock index as k_clock leaves it (for k_frame / diagnostics)
     uint32_t *tiles_done;                // [ng] consumer-warp arrivals per capture (reset by the framing job)
-    uint32_t *ctrl;                      // [2][4] job counters {next clock job, next frame job}, slot = epoch & 1
+    uint32_t *ctrl;                      // [2][4] job counters {next clock job}, slot = epoch & 1
     uint8_t *out;
     AfskRxResult *res;
 };
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
 }
 
 // -------------------------------------------------------------------------- auxiliary warps ----
-// Fused mode.  Every CTA of a demodulator launch carries kAuxWarps extra warps that never touch the sample
+// Fused mode.  Every CTA of a demodulator launch carries two or four extra warps that never touch the sample
 // ring.  Together (all CTAs) they work through two job lists of the launch's capture group, each handed out
 // in capture order by a global counter:
 //   clock jobs  __recoverClockIndex (:322-339) for one capture, by the CTA's auxiliary warps together;
@@ -273,31 +300,32 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
 //               every tile of the capture has arrived on the capture's counter (release / acquire).
 // The arithmetic is the same as in k_clock / k_frame_warp; only the scheduling differs, so the three-kernel
 // path stays as the reference the tests compare this one with (AFSK_OPT_FUSED).
-constexpr int kAuxWarps = 2;
-constexpr int kAuxThreads = 32 * kAuxWarps;
-constexpr int kFusedThreads = kDemodThreads + kAuxThreads;
+// kAW auxiliary warps per CTA: 2 behind the general demodulator (its consumers need up to 77 registers, and
+// two CTAs of 11 warps leave 88), 4 behind the short-window kernels (62-68 registers; their captures are the
+// short ones, which need clock jobs at the highest rate)
+constexpr int kAuxWarpsMax = 4;
+constexpr int kFusedThreads2 = kDemodThreads + 64;
+constexpr int kFusedThreads4 = kDemodThreads + 128;
 constexpr int kAuxPass = 2048;                 // clock candidates per pass (the prefix array covers one pass)
 constexpr int kAuxMaxVec = 304;                // 16-byte vectors of samples per pass: 2048 + 2 bf + 14 <= 2432
 constexpr int kAuxMaxBf = (kAuxMaxVec * 8 - kAuxPass - 14) / 2;   // 185
 constexpr int kAuxChain = 18;                  // candidates per chain (a quarter bit apart), see k_clock
-constexpr int kAuxRounds = (kAuxMaxVec + kAuxThreads - 1) / kAuxThreads;   // vectors per thread and pass
-constexpr int kAuxQueue = 64;
+constexpr int kAuxTileSlots = 64;              // tiles in flight between a CTA's consumer warps' reports (they are at most a ring apart)
 
 struct __align__(16) AuxSmem {
     uint32_t Qs[4 + 8 * kAuxMaxVec];           // Qs[4 + i] = y[0] + ... + y[i], Qs[3] = 0 (as in k_clock)
-    uint32_t warp_tot[kAuxWarps];
-    uint32_t warp_min[kAuxWarps];
+    uint32_t warp_tot[kAuxWarpsMax];
+    uint32_t warp_min[kAuxWarpsMax];
     int job[2];
-    // captures whose last tile retired in THIS CTA, waiting for one of its auxiliary warps (bounded ring;
-    // slot value = capture position + 1, 0 = free)
-    uint32_t q_head, q_tail, done_warps, q_pad;
-    int q_slot[kAuxQueue];
+    int q_pad0[2];
+    uint32_t tile_arr[kAuxTileSlots];          // consumer warps that have reported tile n of this CTA, slot n % kAuxTileSlots
     uint8_t lut[128];
 };
 
+template <int kAW>
 __device__ __forceinline__ void aux_bar()
 {
-    asm volatile("bar.sync 2, %0;" ::"n"(kAuxThreads) : "memory");
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * kAW) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
 {
@@ -309,31 +337,31 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t atom_add_acq_rel_u32(uint32_t *p, uint32_t v)
-{
-    uint32_t old;
-    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
-}
 // plane words written by other CTAs of the same launch: read them from L2 (an L1 line could be stale)
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p)
 {
     uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));    // not volatile: independent loads may be batched
     return v;
 }
 
-// Clock index of one capture by the kAuxThreads auxiliary threads of a CTA (atid = 0 .. kAuxThreads-1).
+// Clock index of one capture by the 32 * kAW auxiliary threads of a CTA (atid = 0 .. 32 kAW - 1).
 // Same closed form and chains as k_clock; differences: the 4096-frame window is scanned in passes of
 // kAuxPass candidates so that the prefix array is 9.7 KB instead of 16.5 KB (the ring of the short-window
 // kernels leaves no more), and the first minimum is found in ONE sweep as the minimum of the key
 // (floor(D / 2bf) << 12) | i, the floor by a multiply-shift that is exact for D < 2^28.
+template <int kAW>
 __device__ uint32_t aux_clock_index(const int16_t *__restrict__ x, long long off, int bf, uint32_t magic, int shift,
                                     AuxSmem &S, int atid)
 {
+    constexpr int kAT = 32 * kAW;
+    constexpr int kRounds = (kAuxMaxVec + kAT - 1) / kAT;       // vectors per thread and pass
     const int lane = atid & 31, warp = atid >> 5;
     const int q = bf >> 2, span = AFSK_SYNC_FRAMES - 2 * bf;    // :327
     const uint32_t c0 = 65535u * (uint32_t)bf;
+    const int qL = q * kAuxChain;
+    // item = chain (block b, residue a): candidates a + qL b, a + qL b + q, ...  (local to the pass)
+    const int b_first = atid / q, a_first = atid - b_first * q;
     uint32_t best = 0xFFFFFFFFu;
     for (int s0 = 0; s0 < span; s0 += kAuxPass) {
         const int C = min(kAuxPass, span - s0);                 // candidates s0 .. s0 + C - 1
@@ -341,20 +369,24 @@ __device__ uint32_t aux_clock_index(const int16_t *__restrict__ x, long long off
         const int e = (int)(g0 - ga);
         const int nvec = (e + C + 2 * bf + 7) >> 3;             // <= kAuxMaxVec (bf <= kAuxMaxBf, checked on the host)
         const uint4 *src = reinterpret_cast<const uint4 *>(x + ga);
-        // warp w scans vectors [w * VW, (w + 1) * VW): kAuxRounds rounds of 32 coalesced 16-byte loads
-        constexpr int VW = kAuxRounds * 32;
+        // warp w scans vectors [w * VW, (w + 1) * VW): kRounds rounds of 32 coalesced 16-byte loads
+        constexpr int VW = kRounds * 32;
         uint32_t carry = 0;
-        uint32_t voff[kAuxRounds];
+        uint32_t voff[kRounds];
+        uint4 qv[kRounds];
 #pragma unroll
-        for (int r = 0; r < kAuxRounds; r++) {
+        for (int r = 0; r < kRounds; r++) {
             const int v = warp * VW + r * 32 + lane;
-            uint4 qv = make_uint4(0u, 0u, 0u, 0u);
-            if (v < nvec) qv = ld_nc_v4(src + v);
+            qv[r] = make_uint4(0u, 0u, 0u, 0u);
+            if (v < nvec) qv[r] = ld_nc_v4(src + v);
+        }
+#pragma unroll
+        for (int r = 0; r < kRounds; r++) {
             // sum of the vector's 8 samples: IDP.2A with weights (1, 1) adds both halves of a word
-            int run = __dp2a_lo((int)qv.x, 0x0101, 0);
-            run = __dp2a_lo((int)qv.y, 0x0101, run);
-            run = __dp2a_lo((int)qv.z, 0x0101, run);
-            run = __dp2a_lo((int)qv.w, 0x0101, run);
+            int run = __dp2a_lo((int)qv[r].x, 0x0101, 0);
+            run = __dp2a_lo((int)qv[r].y, 0x0101, run);
+            run = __dp2a_lo((int)qv[r].z, 0x0101, run);
+            run = __dp2a_lo((int)qv[r].w, 0x0101, run);
             uint32_t inc = (uint32_t)run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -366,16 +398,14 @@ __device__ uint32_t aux_clock_index(const int16_t *__restrict__ x, long long off
         }
         if (lane == 0) S.warp_tot[warp] = carry;
         if (atid == 0) S.Qs[3] = 0;
-        aux_bar();
+        aux_bar<kAW>();
         uint32_t base = 0;
         for (int w = 0; w < warp; w++) base += S.warp_tot[w];
-        // second sweep (the vectors come from L2 again: 4.8 KB per pass): running sums into shared memory
 #pragma unroll
-        for (int r = 0; r < kAuxRounds; r++) {
+        for (int r = 0; r < kRounds; r++) {
             const int v = warp * VW + r * 32 + lane;
             if (v < nvec) {
-                const uint4 qv = ld_nc_v4(src + v);
-                const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
+                const uint32_t wv[4] = {qv[r].x, qv[r].y, qv[r].z, qv[r].w};
                 uint32_t run = base + voff[r], pre[8];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -387,55 +417,72 @@ __device__ uint32_t aux_clock_index(const int16_t *__restrict__ x, long long off
                 dst[1] = make_uint4(pre[4], pre[5], pre[6], pre[7]);
             }
         }
-        aux_bar();
+        aux_bar<kAW>();
         // candidate s0 + il (il < C):  D = c0 + t0 + t8 - 2 (t1 - t2 + t3 - t4 + t6),  t_m = P[il + m q],
-        // P[j] = Qs[3 + e + j].  Item (block b, residue a) is the chain a + q * kAuxChain * b, a + q, ...
+        // P[j] = Qs[3 + e + j]
         const uint32_t *Pe = S.Qs + 3 + e;
-        const int qL = q * kAuxChain;
-        const int nitems = ((C + qL - 1) / qL) * q;
-        for (int it = atid; it < nitems; it += kAuxThreads) {
-            const int st = (it % q) + qL * (it / q);
-            int kv = (C - st + q - 1) / q;                       // valid candidates of the chain
-            if (kv <= 0) continue;
-            kv = kv > kAuxChain ? kAuxChain : kv;
+        int a = a_first, b = b_first;
+        while (true) {
+            const int st = a + qL * b;
+            if (st >= C) break;                                  // blocks only grow from here
             uint32_t t[9];
             uint32_t ta = afsk_smem_u32(Pe + st);
             const uint32_t tstep = 4u * (uint32_t)q;
 #pragma unroll
             for (int m = 0; m < 8; m++) { t[m] = lds_u32(ta); ta += tstep; }
-            uint32_t idx = (uint32_t)(s0 + st);
+            int il = st;
 #pragma unroll
             for (int k = 0; k < kAuxChain; k++) {
-                t[8] = lds_u32_if(ta, k < kv);                  // undefined for k >= kv (never used)
+                const bool valid = il < C;
+                t[8] = lds_u32_if(ta, valid);                   // undefined past the pass (never used)
                 ta += tstep;
                 const uint32_t D = c0 + t[0] + t[8] - 2u * (t[1] - t[2] + t[3] - t[4] + t[6]);
                 const uint32_t fl = (uint32_t)(((unsigned long long)D * magic) >> shift);     // getDiff :107
-                const uint32_t key = (fl << 12) | idx;
-                if (k < kv) best = min(best, key);
-                idx += (uint32_t)q;
+                const uint32_t key = (fl << 12) | (uint32_t)(s0 + il);
+                if (valid) best = min(best, key);
+                il += q;
 #pragma unroll
                 for (int m = 0; m < 8; m++) t[m] = t[m + 1];
             }
+            // next item of this thread: it + kAT
+            a += kAT % q; b += kAT / q;                          // kAT is a constant: one division by q per job
+            if (a >= q) { a -= q; b++; }
         }
-        aux_bar();                                               // the next pass overwrites Qs
+        aux_bar<kAW>();                                          // the next pass overwrites Qs
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
     if (lane == 0) S.warp_min[warp] = best;
-    aux_bar();
+    aux_bar<kAW>();
     best = S.warp_min[0];
 #pragma unroll
-    for (int w = 1; w < kAuxWarps; w++) best = min(best, S.warp_min[w]);
+    for (int w = 1; w < kAW; w++) best = min(best, S.warp_min[w]);
     return best & 4095u;                                         // first index of the minimum (:332-337)
 }
 
-// consumer-side state of fused framing (see signal_step, defined with the framing code below)
+// consumer-side state of fused framing (see signal_flush, defined with the framing code below): a consumer
+// warp notes the capture of every tile it finishes, one tile per lane, and reports 32 of them at a time
 struct TileSignal {
-    int ci = -1;                 // tile finished in the previous iteration, not yet reported
-    uint32_t want = 0;
-    int ci2 = -1;                // reported; the counter value it saw is in old2
-    uint32_t want2 = 0, old2 = 0;
+    int ci = -1;                 // this lane's noted tile: position of its capture in the group
+    uint32_t want = 0;           // tiles that complete that capture
+    int npend = 0;               // tiles noted since the last report (warp-uniform)
+    int n0 = 0;                  // sequence number (in this CTA) of the first noted tile
+    int seq = 0;                 // tiles seen so far
 };
+__device__ __forceinline__ void signal_flush(const DemodParams &p, AuxSmem &S, TileSignal &t, int lane);
+__device__ __forceinline__ void signal_note(const DemodParams &p, AuxSmem &S, TileSignal &t, int ci, uint32_t want, int lane)
+{
+#ifdef AFSK_DBG_NOSIGNAL
+    return;
+#endif
+    if (t.npend == 32) signal_flush(p, S, t, lane);   // the noted tiles' plane stores are at least one tile old
+    if (t.npend == 0) t.n0 = t.seq;
+    if (lane == t.npend) { t.ci = ci; t.want = want; }
+    t.npend++;
+    t.seq++;
+}
+__device__ __forceinline__ void signal_finish(const DemodParams &p, AuxSmem &S, TileSignal &t, int lane);
+template <int kAW>
 __device__ __forceinline__ void demod_aux(const DemodParams &p, uint8_t *smem);
 // before the CTA's first barrier: the framing queue starts empty (the auxiliary threads exist only in fused mode)
 __device__ __forceinline__ void aux_smem_init(const DemodParams &p, AuxSmem &S)
@@ -443,11 +490,8 @@ __device__ __forceinline__ void aux_smem_init(const DemodParams &p, AuxSmem &S)
     if (!p.fused) return;
     const int atid = (int)threadIdx.x - kDemodThreads;
     if (atid < 0) return;
-    if (atid == 0) { S.q_head = 0u; S.q_tail = 0u; S.done_warps = 0u; }
-    for (int i = atid; i < kAuxQueue; i += kAuxThreads) S.q_slot[i] = 0;
+    for (int i = atid; i < kAuxTileSlots; i += 64) S.tile_arr[i] = 0u;
 }
-__device__ __forceinline__ void signal_step(const DemodParams &p, AuxSmem &S, TileSignal &t, int new_ci, uint32_t new_want, int lane);
-__device__ __forceinline__ void signal_finish(const DemodParams &p, AuxSmem &S, TileSignal &t, int lane);
 
 // ------------------------------------------------------------------------------ k_demod ----
 // Per-sample classification (Receiver.__amplify :287-296) and the two getDiff sums (:346-347)
@@ -601,7 +645,7 @@ __device__ __forceinline__ TileJob demod_tile_job(const DemodParams &p, int it, 
     j.m.thr_bf = thr * p.bf;
     j.m.gpos = ci;
     j.m.word_base = plane_base + (k0t >> 5);
-    j.m.want = (uint32_t)(kConsumerThreads / 32) * (uint32_t)(p.gtile_first[ci + 1] - first);
+    j.m.want = (uint32_t)(p.gtile_first[ci + 1] - first);
     j.m.pad2 = 0;
     j.ga = ga;
     j.bytes = nwin > 0 ? (uint32_t)((((long long)j.m.e0 + (long long)nwin * p.bf) * 2 + 15) & ~15LL) : 0u;
@@ -658,7 +702,7 @@ __device__ __forceinline__ void demod_produce(const DemodParams &p, int ntile, u
 // kMerge: the thread segment is a multiple of 8 samples, so the partial head vector (slots >= e)
 // and the partial tail vector (slots < e) are merged into one full vector with 4 PRMTs.
 template <int kNT, bool kMerge>
-__global__ void __launch_bounds__(kFusedThreads, 2) k_demod(const DemodParams p)
+__global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -735,7 +779,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_demod(const DemodParams p)
         return;
     }
     if (warp > kConsumerThreads / 32) {
-        demod_aux(p, smem);
+        demod_aux<2>(p, smem);
         return;
     }
     TileSignal sig;
@@ -757,7 +801,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_demod(const DemodParams p)
     for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
-        if (p.fused_frame) signal_step(p, AS, sig, m.gpos, m.want, lane);
+        if (p.fused_frame) signal_note(p, AS, sig, m.gpos, m.want, lane);
         bool bit = false, quiet = false;
         if (m.nwin > 0) {
             const int rel = m.e0 + rel0;
@@ -1000,7 +1044,7 @@ __device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int
 }
 
 template <int kBf, int kWpt>
-__global__ void __launch_bounds__(kFusedThreads, 2) k_demod_shift(const DemodParams p)
+__global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodParams p)
 {
     static_assert(kBf % 4 == 0 && (kBf * kWpt) % 8 == 0 && 32 % kWpt == 0, "segment must be whole vectors");
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1030,7 +1074,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_demod_shift(const DemodPar
         return;
     }
     if (warp > kConsumerThreads / 32) {
-        demod_aux(p, smem);
+        demod_aux<4>(p, smem);
         return;
     }
     TileSignal sig;
@@ -1041,7 +1085,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_demod_shift(const DemodPar
     for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
-        if (p.fused_frame) signal_step(p, AS, sig, m.gpos, m.want, lane);
+        if (p.fused_frame) signal_note(p, AS, sig, m.gpos, m.want, lane);
         uint32_t bits = 0, quiet = 0;
         if (m.nwin > 0) {
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) + tid * (kSeg / 8);
@@ -1185,7 +1229,7 @@ __device__ __forceinline__ void lane_decode(const uint4 *dp, uint32_t k512, int 
 }
 
 template <int kM, int kJ, int kWarps>
-__global__ void __launch_bounds__(kWarps * 32 + 32 + kAuxThreads, 2) k_demod_lane(const DemodParams p)
+__global__ void __launch_bounds__(kWarps * 32 + 32 + 128, 2) k_demod_lane(const DemodParams p)
 {
     static_assert(kJ * 32 * kWarps * 8 * kM * 2 <= 64 * 1024, "tile");
     static_assert(kWarps * 32 == kConsumerThreads, "the auxiliary warps follow the producer warp");
@@ -1215,7 +1259,7 @@ __global__ void __launch_bounds__(kWarps * 32 + 32 + kAuxThreads, 2) k_demod_lan
         return;
     }
     if (warp > kWarps) {
-        demod_aux(p, smem);
+        demod_aux<4>(p, smem);
         return;
     }
     TileSignal sig;
@@ -1227,7 +1271,7 @@ __global__ void __launch_bounds__(kWarps * 32 + 32 + kAuxThreads, 2) k_demod_lan
     for (int n = 0; n < ntile; ++n) {
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
-        if (p.fused_frame) signal_step(p, AS, sig, m.gpos, m.want, lane);
+        if (p.fused_frame) signal_note(p, AS, sig, m.gpos, m.want, lane);
         uint32_t bw[kJ], qw[kJ];
 #pragma unroll
         for (int j = 0; j < kJ; j++) { bw[j] = 0u; qw[j] = 0u; }
@@ -1295,6 +1339,7 @@ __device__ __forceinline__ uint32_t hamming74_nibble(uint32_t cw)
 // lut[cw] = corrected nibble of codeword cw (128 entries, built per CTA)
 __device__ __forceinline__ uint32_t decode_byte(uint32_t v14, const uint8_t *lut)
 {
+
     return ((uint32_t)lut[v14 & 0x7Fu] << 4) | (uint32_t)lut[(v14 >> 7) & 0x7Fu];
 }
 
@@ -1422,19 +1467,29 @@ __device__ __forceinline__ void frame_capture_warp(int c, const CapDesc &d, int 
     const uint32_t *PW = reinterpret_cast<const uint32_t *>(planes + d.plane_base);   // word j: bits PW[2j], quiet PW[2j + 1]
     constexpr unsigned NONE = 0x7FFFFFFFu;
     constexpr int kWords = 8;                           // plane words per lane per step (loads in flight)
+    AFSK_TRACE_DECL
+    AFSK_TRACE_MARK
 
+    // Every step issues all of its loads before it looks at any of them: a frame job of the fused kernel runs
+    // on one warp beside a saturated memory system, where a dependent L2 round trip costs microseconds.
     // phase 1 (:362-366): first k with bits[k-3..k] == 1,0,0,0 ; the shift register starts at 0
     unsigned kterm = NONE;
     for (int base = 0; base < nwords; base += 32 * kWords) {
+        uint32_t cur[kWords], prv[kWords];
+#pragma unroll
+        for (int r = 0; r < kWords; r++) {
+            const int j = base + lane + 32 * r;
+            cur[r] = j < nwords ? plane_word<kCg>(PW + 2 * j) : 0u;
+            prv[r] = (j < nwords && j > 0) ? plane_word<kCg>(PW + 2 * j - 2) : 0u;
+        }
         unsigned cand = NONE;
 #pragma unroll
         for (int r = kWords - 1; r >= 0; r--) {
             const int j = base + lane + 32 * r;
             if (j < nwords) {
-                const uint32_t cur = plane_word<kCg>(PW + 2 * j), prev = j ? plane_word<kCg>(PW + 2 * j - 2) : 0u;
                 // bit t of M: b[k-3] & ~b[k-2] & ~b[k-1] & ~b[k] for k = 32j + t
-                uint32_t M = __funnelshift_l(prev, cur, 3) & ~__funnelshift_l(prev, cur, 2) &
-                             ~__funnelshift_l(prev, cur, 1) & ~cur;
+                uint32_t M = __funnelshift_l(prv[r], cur[r], 3) & ~__funnelshift_l(prv[r], cur[r], 2) &
+                             ~__funnelshift_l(prv[r], cur[r], 1) & ~cur[r];
                 const int rem = K - 32 * j;
                 if (rem < 32) M &= (1u << rem) - 1u;
                 if (M) cand = (unsigned)(32 * j + (__ffs(M) - 1));
@@ -1444,15 +1499,22 @@ __device__ __forceinline__ void frame_capture_warp(int c, const CapDesc &d, int 
         if (kterm != NONE) break;
     }
     const int k0 = (kterm == NONE) ? K : (int)kterm + 1;
+    AFSK_TRACE_MARK
     // phase 2 (:372-378): first quiet window at or after k0
     unsigned kq = NONE;
     for (int base = k0 >> 5; base < nwords; base += 32 * kWords) {
+        uint32_t qw[kWords];
+#pragma unroll
+        for (int r = 0; r < kWords; r++) {
+            const int j = base + lane + 32 * r;
+            qw[r] = j < nwords ? plane_word<kCg>(PW + 2 * j + 1) : 0u;
+        }
         unsigned cand = NONE;
 #pragma unroll
         for (int r = kWords - 1; r >= 0; r--) {
             const int j = base + lane + 32 * r;
             if (j < nwords) {
-                uint32_t M = plane_word<kCg>(PW + 2 * j + 1);
+                uint32_t M = qw[r];
                 if (j == (k0 >> 5)) M &= ~((1u << (k0 & 31)) - 1u);
                 const int rem = K - 32 * j;
                 if (rem < 32) M &= (1u << rem) - 1u;
@@ -1463,32 +1525,46 @@ __device__ __forceinline__ void frame_capture_warp(int c, const CapDesc &d, int 
         if (kq != NONE) break;
     }
     const int k1 = (kq == NONE) ? K : (int)kq;
+    AFSK_TRACE_MARK
     const int nbits = k1 - k0;
     const int nbytes = (nbits / 7) / 2;              // ECC.decode :156, __bitsToBytes :396
     uint8_t *o = out + d.out_off;                    // 16-byte aligned
-    // four bytes (56 coded bits) per lane step: three plane words, one 32-bit store
+    // four bytes (56 coded bits) per lane step: three plane words, one 32-bit store; four steps' loads at a time
     const int nquad = nbytes >> 2;
-#pragma unroll 2
-    for (int i = lane; i < nquad; i += 32) {
-        const int pos = k0 + 56 * i;
-        const int wi = pos >> 5;
-        const uint32_t sh = (uint32_t)(pos & 31);
-        const uint32_t w0 = plane_word<kCg>(PW + 2 * wi), w1 = plane_word<kCg>(PW + 2 * wi + 2), w2 = plane_word<kCg>(PW + 2 * wi + 4);
-        uint32_t word = 0;
+    constexpr int kQ = 4;
+    for (int i0 = lane; i0 < nquad; i0 += 32 * kQ) {
+        uint32_t w[kQ][3];
 #pragma unroll
-        for (int jb = 0; jb < 4; jb++) {
-            const uint32_t sft = sh + 14u * jb;                 // 0 .. 73
-            const uint32_t a = sft < 32 ? w0 : (sft < 64 ? w1 : w2);
-            const uint32_t bb = sft < 32 ? w1 : (sft < 64 ? w2 : 0u);
-            word |= decode_byte(__funnelshift_r(a, bb, sft & 31u) & 0x3FFFu, lut) << (8 * jb);
+        for (int u = 0; u < kQ; u++) {
+            const int i = i0 + 32 * u;
+            const int wi = (k0 + 56 * i) >> 5;
+#pragma unroll
+            for (int t = 0; t < 3; t++) w[u][t] = i < nquad ? plane_word<kCg>(PW + 2 * (wi + t)) : 0u;
         }
-        reinterpret_cast<uint32_t *>(o)[i] = word;
+#pragma unroll
+        for (int u = 0; u < kQ; u++) {
+            const int i = i0 + 32 * u;
+            if (i < nquad) {
+                const uint32_t sh = (uint32_t)((k0 + 56 * i) & 31);
+                uint32_t word = 0;
+#pragma unroll
+                for (int jb = 0; jb < 4; jb++) {
+                    const uint32_t sft = sh + 14u * jb;                 // 0 .. 73
+                    const uint32_t a = sft < 32 ? w[u][0] : (sft < 64 ? w[u][1] : w[u][2]);
+                    const uint32_t bb = sft < 32 ? w[u][1] : (sft < 64 ? w[u][2] : 0u);
+                    word |= decode_byte(__funnelshift_r(a, bb, sft & 31u) & 0x3FFFu, lut) << (8 * jb);
+                }
+                reinterpret_cast<uint32_t *>(o)[i] = word;
+            }
+        }
     }
     for (int i = 4 * nquad + lane; i < nbytes; i += 32) {
         const int pos = k0 + 14 * i;
         const uint32_t lo = plane_word<kCg>(PW + 2 * (pos >> 5)), hi = plane_word<kCg>(PW + 2 * (pos >> 5) + 2);
         o[i] = (uint8_t)decode_byte(__funnelshift_r(lo, hi, (uint32_t)(pos & 31)) & 0x3FFFu, lut);
     }
+    AFSK_TRACE_MARK
+    if ((c & 7) == 0) { AFSK_TRACE_EMIT((kCg ? 2ull : 3ull) + ((unsigned long long)blockIdx.x << 8)) }
     if (lane == 0) {
         AfskRxResult r;
         r.status = nbits > 0 ? AFSK_ST_OK : AFSK_ST_NO_DATA;
@@ -1534,98 +1610,122 @@ __global__ void __launch_bounds__(256) k_preset(const CapDesc *__restrict__ caps
 }
 
 // The auxiliary warps of one CTA of a fused demodulator launch (see "auxiliary warps" above).
-__device__ __forceinline__ bool aux_pop_and_frame(const DemodParams &p, AuxSmem &S, int lane)
+// Framing is dealt out statically: auxiliary warp gw of the launch (gw = CTA * kAW + warp) frames captures
+// gw, gw + W, gw + 2W, ... of the group (W = auxiliary warps of the whole launch), in that order, each as soon
+// as its tile counter shows every tile reported.  (Measured alternatives: letting the CTA whose report
+// completes a capture frame it hands hundreds of captures to the one CTA that reports last in every report
+// interval; one launch-wide queue popped by compare-and-swap collapses under 1,184 pollers.)
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
 {
-    // claims one queued capture (if any) for this warp and frames it
-    int v = 0;
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// frames capture position ci if all of its tiles have been reported; false otherwise (nothing waits here)
+__device__ __forceinline__ bool aux_try_frame(const DemodParams &p, AuxSmem &S, int ci, int lane)
+{
+    uint32_t ready = 0;
     if (lane == 0) {
-        while (true) {
-            const uint32_t h = *reinterpret_cast<volatile uint32_t *>(&S.q_head);
-            if (h == *reinterpret_cast<volatile uint32_t *>(&S.q_tail)) break;
-            if (atomicCAS(&S.q_head, h, h + 1u) != h) continue;
-            // the pusher took its ticket before it wrote the slot
-            while ((v = atomicExch(&S.q_slot[h % kAuxQueue], 0)) == 0) __nanosleep(64);
-            break;
-        }
-        __threadfence_block();                        // acquire: the pusher's acquire of the capture's tiles
+        const uint32_t want = (uint32_t)(p.gtile_first[ci + 1] - p.gtile_first[ci]);
+        ready = ld_acquire_u32(p.tiles_done + ci) == want;        // acquire: every CTA's plane words of the capture
+        if (ready) p.tiles_done[ci] = 0u;                          // nobody touches the counter again in this launch
     }
-    v = __shfl_sync(0xFFFFFFFFu, v, 0);
-    if (v == 0) return false;
-    const int c = p.gcaps[v - 1];
+    if (!__shfl_sync(0xFFFFFFFFu, ready, 0)) return false;
+    const int c = p.gcaps[ci];
     const CapDesc d = p.caps[c];
     const int clk = (int)(uint32_t)ld_relaxed_u64(p.cready + c);
+#ifndef AFSK_DBG_NOFRAME
     frame_capture_warp<true>(c, d, clk, p.planes, p.out, p.res, S.lut, lane);
+#endif
     return true;
 }
 
+template <int kAW>
 __device__ __forceinline__ void demod_aux(const DemodParams &p, uint8_t *smem)
 {
+    constexpr int kAT = 32 * kAW;
     AuxSmem &S = *reinterpret_cast<AuxSmem *>(smem + p.aux_off);
     const int atid = (int)threadIdx.x - kDemodThreads, lane = atid & 31;
     uint32_t *ctrl = p.ctrl + 4 * (p.epoch & 1u);
     if (blockIdx.x == 0 && atid == 0) {               // the other slot serves the next launch of this group
         uint32_t *other = p.ctrl + 4 * ((p.epoch + 1u) & 1u);
-        other[0] = 0u; other[1] = 0u;
+        other[0] = 0u;
     }
+    if (p.fused_frame)                                // Hamming(7,4) nibble table; visible after the first aux_bar below
+        for (int i = atid; i < 128; i += kAT) S.lut[i] = (uint8_t)hamming74_nibble((uint32_t)i);
+    // this warp's framing list: captures fnext, fnext + fstride, ... of the group
+    const int fstride = (int)gridDim.x * kAW;
+    int fnext = (int)blockIdx.x * kAW + (atid >> 5);
     // ---- clock jobs, in capture order, the auxiliary warps of the CTA together; between two clock jobs
-    //      every warp frames at most one capture that has retired in this CTA meanwhile ----
+    //      every warp frames the next capture of its list if that one is complete ----
     for (int it = 0;; it++) {
         if (atid == 0) S.job[it & 1] = (int)atomicAdd(&ctrl[0], 1u);
-        aux_bar();
+        aux_bar<kAW>();
         const int j = S.job[it & 1];
         if (j >= p.ng) break;
         const int c = p.gcaps[j];
         const long long off = p.caps[c].off;
-        const uint32_t clk = aux_clock_index(p.samples, off, p.bf, p.clk_magic, p.clk_shift, S, atid);
+        AFSK_TRACE_DECL
+        AFSK_TRACE_MARK
+        const uint32_t clk = aux_clock_index<kAW>(p.samples, off, p.bf, p.clk_magic, p.clk_shift, S, atid);
+        AFSK_TRACE_MARK
+        if (atid == 0) { AFSK_TRACE_EMIT(1ull) }
         if (atid == 0) {
             p.clock_out[c] = (int32_t)clk;
             st_relaxed_u64(p.cready + c, ((unsigned long long)p.epoch << 32) | clk);
         }
-        if (p.fused_frame) aux_pop_and_frame(p, S, lane);
+        if (p.fused_frame && fnext < p.ng && aux_try_frame(p, S, fnext, lane)) fnext += fstride;
     }
     if (!p.fused_frame) return;
-    // ---- the rest of the CTA's captures, until its consumer warps are gone and the queue is empty ----
-    while (true) {
-        if (aux_pop_and_frame(p, S, lane)) continue;
-        const uint32_t done = *reinterpret_cast<volatile uint32_t *>(&S.done_warps);
-        if (done == (uint32_t)(kConsumerThreads / 32) &&
-            *reinterpret_cast<volatile uint32_t *>(&S.q_head) == *reinterpret_cast<volatile uint32_t *>(&S.q_tail))
-            break;
-        __nanosleep(200);
+    // ---- the rest of the list.  A capture completes when the consumer warps of every CTA holding one of its
+    //      tiles have reported: this waits for other CTAs, all of which are resident (the grid is sized to
+    //      the device's capacity for this kernel). ----
+    uint32_t backoff = 100;
+    while (fnext < p.ng) {
+        if (aux_try_frame(p, S, fnext, lane)) { fnext += fstride; backoff = 100; continue; }
+        __nanosleep(backoff);
+        backoff = backoff < 1600 ? backoff * 2 : backoff;
+    }
+    {
+        AFSK_TRACE_DECL
+        AFSK_TRACE_MARK
+        AFSK_TRACE_MARK
+        if (atid == 0) { AFSK_TRACE_EMIT(6ull + ((unsigned long long)blockIdx.x << 8)) }
     }
 }
 
-// Consumer side of fused framing.  A consumer warp reports a finished tile to the tile's capture one
-// iteration late (its plane stores have long landed by then, so the release costs no wait) and reads the
-// answer of that report another iteration later (so the atomic's round trip is never waited for either).
-// The warp whose arrival completes a capture queues it for the CTA's auxiliary warps.
-__device__ __forceinline__ void aux_push(AuxSmem &S, int ci)
+// Consumer side of fused framing.  Reporting a finished tile to its capture's counter needs a release at
+// GPU scope (the plane words must be visible to whichever CTA frames the capture).  A fence per tile and
+// warp costs more than the tile, and one atomic per tile and warp crowds the L2 atomic unit of the few
+// counters the whole grid is working on.  So a consumer warp only NOTES its tiles (signal_note, one per
+// lane) and reports 32 at a time: fence (its own plane stores), then every lane arrives on the tile's slot in
+// shared memory; the lane whose arrival is the CTA's last for the tile (all consumer warps have fenced and
+// arrived) fences again (the arrivals it observed -> its own report) and adds ONE to the capture's counter.
+__device__ __forceinline__ void signal_flush(const DemodParams &p, AuxSmem &S, TileSignal &t, int lane)
 {
-    __threadfence_block();                            // release: what this thread acquired goes with the slot
-    const uint32_t t = atomicAdd(&S.q_tail, 1u);
-    while (atomicCAS(&S.q_slot[t % kAuxQueue], 0, ci + 1) != 0) __nanosleep(64);   // ring full: the CTA's auxiliary warps drain it
-}
-
-__device__ __forceinline__ void signal_step(const DemodParams &p, AuxSmem &S, TileSignal &t, int new_ci, uint32_t new_want, int lane)
-{
-    __syncwarp();                                     // the other lanes' plane stores of the previous tile
-    if (lane == 0) {
-        if (t.ci2 >= 0 && t.old2 + 1u == t.want2) {
-            p.tiles_done[t.ci2] = 0u;                 // last arrival: nobody touches the counter again in this launch
-            aux_push(S, t.ci2);
+    if (t.npend == 0) return;
+    __syncwarp();                                     // the other lanes' plane stores
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    const bool mine = lane < t.npend;
+    bool cta_last = false;
+    uint32_t *slot = &S.tile_arr[(t.n0 + lane) % kAuxTileSlots];
+    if (mine) cta_last = atomicAdd(slot, 1u) == (uint32_t)(kConsumerThreads / 32 - 1);
+    if (__any_sync(0xFFFFFFFFu, cta_last)) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (cta_last) {
+            *slot = 0u;                               // the slot's next user is kAuxTileSlots tiles away
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.tiles_done + t.ci) : "memory");
         }
-        t.ci2 = t.ci; t.want2 = t.want;
-        if (t.ci >= 0) t.old2 = atom_add_acq_rel_u32(p.tiles_done + t.ci, 1u);
-        t.ci = new_ci; t.want = new_want;
     }
+    __syncwarp();
+    t.npend = 0;
 }
 
 // after a consumer warp's last tile
 __device__ __forceinline__ void signal_finish(const DemodParams &p, AuxSmem &S, TileSignal &t, int lane)
 {
-    signal_step(p, S, t, -1, 0u, lane);
-    signal_step(p, S, t, -1, 0u, lane);
-    if (lane == 0) atomicAdd(&S.done_warps, 1u);
+    signal_flush(p, S, t, lane);
 }
 
 // ------------------------------------------------------------------------------- k_gate ----
@@ -1815,6 +1915,21 @@ static void launch_demod(int merge, int nt, int grid, int block, size_t smem, cu
     k_demod<0, false><<<grid, block, smem, st>>>(q);
 }
 
+// the kernel a group is demodulated with (same selection as the launch), for occupancy queries
+static const void *demod_kernel_of(const Group &g)
+{
+    if (g.small_wpt && g.bf == 8) return (const void *)k_demod_lane<1, 8, 8>;
+    if (g.small_wpt && g.bf == 16) return (const void *)k_demod_lane<2, 4, 8>;
+    if (g.small_wpt && g.bf == 24) return (const void *)k_demod_lane<3, 2, 8>;
+    if (g.shift_wpt && g.bf == 12) return (const void *)k_demod_shift<12, 4>;
+    if (g.shift_wpt && g.bf == 20) return (const void *)k_demod_shift<20, 2>;
+#define X(NT, MG) \
+    if ((MG) == (g.merge != 0) && (NT) == g.nt) return (const void *)k_demod<NT, MG>;
+    AFSK_DEMOD_VARIANTS(X)
+#undef X
+    return (const void *)k_demod<0, false>;
+}
+
 struct AfskRxPlan {
     int device = 0;
     int B = 0;
@@ -1839,7 +1954,7 @@ struct AfskRxPlan {
     int n_preset = 0;             // captures whose result is decided on the host (status0 != 0)
     int64_t sum_samples = 0;      // over the captures decoded on the GPU
     bool can_fuse = false;        // every group fits the auxiliary warps (bit length, shared memory)
-    int fused = -1;               // AFSK_OPT_FUSED: -1 automatic, 0 three kernels, 1 fused whenever possible
+    int fused = -1;               // AFSK_OPT_FUSED: -1 automatic, 0 three kernels, 1 fused clocks, 2 fused clocks and framing
     int frame_kernel = 0;         // AFSK_OPT_FRAME_KERNEL: 0 automatic, 1 k_frame_warp, 2 k_frame<128,4,int>, 3 <512,8,int>, 4 <512,8,long long>
     int l2_hint = -1;             // AFSK_OPT_L2_HINT / AFSK_L2_HINT (read once per plan): -1 per-kernel default
     bool timing = false;
@@ -2108,6 +2223,19 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
             e = demod_set_smem_attr();
             if (e == cudaSuccess && P->device >= 0 && P->device < 64) attr_set[P->device] = true;
         }
+        // Fused framing waits for other CTAs of the launch: every CTA must be resident.  Ask the runtime how many
+        // CTAs of the group's kernel an SM really holds (registers, threads, shared memory) and size the grid to it.
+        for (size_t gi = 0; gi < P->groups.size() && e == cudaSuccess; gi++) {
+            Group &g = P->groups[gi];
+            if (!g.can_fuse) continue;
+            const int block = (g.small_wpt || g.shift_wpt) ? kFusedThreads4 : kFusedThreads2;
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, demod_kernel_of(g), block, g.smem_fused) != cudaSuccess) nb = 0;
+            (void)cudaGetLastError();
+            const int per_sm_f = std::min(nb, g.smem_fused <= 113 * 1024 ? 2 : 1);
+            if (per_sm_f < 1) { g.can_fuse = false; P->can_fuse = false; continue; }
+            g.grid_fused = std::max(1, std::min((int)g.tile_first.back(), P->sm_count * per_sm_f));
+        }
     }
     // the set-up ran on the legacy default stream; decodes may use non-blocking streams
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
@@ -2153,7 +2281,9 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     const char *ev = getenv("AFSK_L2_HINT");            // tuning overrides, read once per plan
     if (ev) P->l2_hint = atoi(ev);
     ev = getenv("AFSK_FUSED");
-    if (ev) P->fused = atoi(ev) < 0 ? -1 : (atoi(ev) ? 1 : 0);
+    if (ev) P->fused = atoi(ev) < 0 ? -1 : std::min(atoi(ev), 2);
+    ev = getenv("AFSK_FRAME_KERNEL");
+    if (ev && atoi(ev) >= 0 && atoi(ev) <= 4) P->frame_kernel = atoi(ev);
     const int rc = plan_build(P, B, h_start, h_len, h_baud, h_amp_end);
     if (rc != AFSK_OK) { afsk_rx_plan_destroy(P); return rc; }
     *plan_out = P;
@@ -2204,7 +2334,8 @@ int afsk_rx_plan_set_option(AfskRxPlan *P, int option, int value)
         P->l2_hint = value < 0 ? -1 : (value ? 1 : 0);
         return AFSK_OK;
     case AFSK_OPT_FUSED:
-        P->fused = value < 0 ? -1 : (value ? 1 : 0);
+        if (value > 2) { afsk_set_error("AFSK_OPT_FUSED: -1..2"); return AFSK_E_ARG; }
+        P->fused = value < 0 ? -1 : value;
         return AFSK_OK;
     default:
         afsk_set_error("afsk_rx_plan_set_option: unknown option %d", option);
@@ -2219,19 +2350,27 @@ int afsk_rx_plan_out_offsets(const AfskRxPlan *P, const int64_t **h_out_off)
     return AFSK_OK;
 }
 
-// which of the two schedules a decode of this plan uses (see "auxiliary warps")
-static bool plan_fused(const AfskRxPlan *P)
+// which schedule a decode of this plan uses (see "auxiliary warps"): 0 three kernels, 1 clocks recovered by the
+// demodulator's auxiliary warps, 2 clocks and framing
+static int plan_fused_level(const AfskRxPlan *P)
 {
-    if (!P->can_fuse || P->fused == 0) return false;
-    if (P->fused == 1) return true;
-    // automatic: the auxiliary warps of the whole grid retire about 45 captures per microsecond (clock + framing),
-    // the stream 3.3 G samples per millisecond: captures must average 73 K samples for the jobs to hide under it
-    return P->sum_samples >= (int64_t)98304 * std::max<int64_t>(P->gpu_caps, 1);
+    if (!P->can_fuse || P->fused == 0) return 0;
+    int level = P->fused;
+    if (level < 0) {
+        // automatic = three kernels.  Measured on B200, same box, alternating runs (profiles/r2_tuning_log.md):
+        //   level 1 (fused clocks): c2 (602 K-frame captures) 0.768 ms against 0.768 — the 24 us of k_clock come back as
+        //   a later start of the stream (the first tiles wait ~10 us for the first round of clock jobs) and as issue
+        //   slots taken from the consumers; c3 (143 K-frame captures) 1.07 ms against 0.82: 55 clock jobs of ~8 us per
+        //   CTA, 3,500 warp instructions each, in a kernel that is already short of issue slots.
+        //   level 2 (fused framing too): c2 0.769 against 0.737, c3 1.05 against 0.81 — the consumer warps' reports cost
+        //   two GPU-scope fences per 32 tiles, more than k_frame_warp takes on an idle GPU.
+        level = 0;
+    }
+    if (level >= 2 && (P->max_windows > kFrameWarpMaxWindows || P->frame_kernel > 1)) level = 1;
+    return level;
 }
-static bool plan_fused_frame(const AfskRxPlan *P)
-{
-    return plan_fused(P) && P->max_windows <= kFrameWarpMaxWindows && P->frame_kernel <= 1;
-}
+static bool plan_fused(const AfskRxPlan *P) { return plan_fused_level(P) >= 1; }
+static bool plan_fused_frame(const AfskRxPlan *P) { return plan_fused_level(P) >= 2; }
 
 int afsk_rx_plan_launches(const AfskRxPlan *P, int *launches)
 {
@@ -2314,7 +2453,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         p.cready = P->d_cready; p.clock_out = P->d_clock; p.tiles_done = g.d_tiles_done; p.ctrl = g.d_ctrl;
         p.out = d_out; p.res = d_res;
         const int grid = fused ? g.grid_fused : g.grid;
-        const int block = fused ? kFusedThreads : kDemodThreads;
+        const int block = !fused ? kDemodThreads : ((g.small_wpt || g.shift_wpt) ? kFusedThreads4 : kFusedThreads2);
         const size_t smem = fused ? g.smem_fused : g.smem;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
@@ -2435,6 +2574,19 @@ int afsk_rx_decode_host(int device, const int16_t *h_samples, const int64_t *h_o
     if (e != cudaSuccess) { afsk_set_error("afsk_rx_decode_host: %s", cudaGetErrorString(e)); return AFSK_E_CUDA; }
     return rc;
 }
+
+#ifdef AFSK_DBG_TRACE
+int afsk_dbg_trace_read(unsigned long long *h_out, int max_records, int reset)
+{
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+    if (n > (1u << 12)) n = 1u << 12;
+    if ((int)n > max_records) n = (unsigned)max_records;
+    if (n) cudaMemcpyFromSymbol(h_out, g_trace, sizeof(unsigned long long) * 10 * n);
+    if (reset) { unsigned int z = 0; cudaMemcpyToSymbol(g_trace_n, &z, sizeof(z)); }
+    return (int)n;
+}
+#endif
 
 /* releases what afsk_rx_decode_host keeps per device between calls */
 int afsk_rx_host_release(int device)

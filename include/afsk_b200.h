@@ -116,11 +116,13 @@ int afsk_rx_plan_destroy(AfskRxPlan *plan);
                                    indices (automatic from 2^30 windows per capture).  A variant that cannot
                                    represent the batch is replaced by the automatic choice. */
 #define AFSK_OPT_L2_HINT 2      /* L2 evict-first hint on the demodulator's bulk copies: -1 per-kernel default, 0, 1 */
-#define AFSK_OPT_FUSED 3        /* schedule of a decode: 1 = one launch per bit length in which auxiliary warps of the
-                                   streaming kernel recover the clocks and frame the captures, 0 = three kernels
-                                   (clock, demodulate, frame), -1 automatic (fused when the captures average
-                                   >= 96 K frames).  Bit lengths over 185 frames (below 260 baud) and captures of
-                                   more than 2^18 bit windows keep the separate kernels for the part concerned. */
+#define AFSK_OPT_FUSED 3        /* schedule of a decode.  0: three kernels (clock, demodulate, frame).  1: auxiliary warps
+                                   of the streaming kernel recover the clocks (no k_clock launch).  2: they also frame
+                                   every capture as soon as its last tile has retired (one launch per bit length).
+                                   -1 automatic = 0 (neither fused level beat the three kernels on a B200, see
+                                   profiles/r2_tuning_log.md; both stay available and parity-tested).  Bit lengths over
+                                   185 frames (below 260 baud) keep the three kernels; captures of more than 2^18 bit
+                                   windows keep the separate framing kernel. */
 int afsk_rx_plan_set_option(AfskRxPlan *plan, int option, int value);
 /* capacity offsets (bytes, B+1 entries, host memory owned by the plan) of the decoded output */
 int afsk_rx_plan_out_offsets(const AfskRxPlan *plan, const int64_t **h_out_off);

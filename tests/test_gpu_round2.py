@@ -295,13 +295,13 @@ def test_fused_equals_three_kernels_and_oracle_mixed():
     caps, baud, thr, _ = _mixed_corpus(51, 160, bauds=(300, 600, 1200, 2400, 4000, 6000, 4800, 9600, 1500, 800, 2000, 3000, 375))
     samples, offsets = A.modem._concat(caps)
     three, n3 = _decode_with(samples, offsets, baud, thr, 0)
-    fused, nf = _decode_with(samples, offsets, baud, thr, 1, repeats=4)
+    fused, nf = _decode_with(samples, offsets, baud, thr, 2, repeats=4)
     assert nf < n3, (nf, n3)                      # one launch per bit length (+ the preset kernel), no k_clock / k_frame
     assert np.array_equal(three.results, fused.results)
     assert three.payloads() == fused.payloads()
     _assert_equals_oracle(fused, caps, baud, thr)
     # fused clocks with a separate framing kernel
-    half, nh = _decode_with(samples, offsets, baud, thr, 1, frame_kernel=2)
+    half, nh = _decode_with(samples, offsets, baud, thr, 1)
     assert nh == nf + 1
     assert np.array_equal(three.results, half.results) and three.payloads() == half.payloads()
 
@@ -325,7 +325,7 @@ def test_fused_many_short_captures_and_every_start_alignment():
     thr = np.full(len(caps), 14000, np.int32)
     samples, offsets = A.modem._concat(caps)
     three, _ = _decode_with(samples, offsets, baud, thr, 0)
-    fused, _ = _decode_with(samples, offsets, baud, thr, 1, repeats=3)
+    fused, _ = _decode_with(samples, offsets, baud, thr, 2, repeats=3)
     assert np.array_equal(three.results, fused.results) and three.payloads() == fused.payloads()
     for i in list(range(0, 6000, 97)) + [100, 200]:
         o = O.rx_decode(caps[i], 6000, 14000)
@@ -353,7 +353,7 @@ def test_fused_clock_every_baud_and_offset(baud):
     b = np.full(len(caps), baud, np.int32)
     thr = np.full(len(caps), 14000, np.int32)
     samples, offsets = A.modem._concat(caps)
-    fused, _ = _decode_with(samples, offsets, b, thr, 1)
+    fused, _ = _decode_with(samples, offsets, b, thr, 2)
     _assert_equals_oracle(fused, caps, b, thr)
 
 
@@ -366,13 +366,13 @@ def test_fused_long_capture_and_retargeted_plan():
     long_cap = np.clip(long_cap.astype(np.int32) + np.round(rng.normal(0, 6000, len(long_cap))).astype(np.int32), -32768, 32767).astype(np.int16)
     shorts, baud, thr, _ = _mixed_corpus(55, 30, bauds=(6000, 1200))
     rx = A.Receiver(6000)
-    os.environ["AFSK_FUSED"] = "1"
+    os.environ["AFSK_FUSED"] = "2"
     try:
         for caps, bd, th in (([long_cap], np.array([6000], np.int32), np.array([14000], np.int32)), (shorts, baud, thr),
                              ([long_cap, shorts[0]], np.array([6000, baud[0]], np.int32), np.array([14000, thr[0]], np.int32)),
                              (shorts[:3], baud[:3], thr[:3])):
             b = rx.decode_batch(caps, baud_rate=bd, amp_end_threshold=th)
-            _cabi.check(_cabi.lib().afsk_rx_plan_set_option(rx._cache[1].plan, _cabi.OPT_FUSED, 1))
+            _cabi.check(_cabi.lib().afsk_rx_plan_set_option(rx._cache[1].plan, _cabi.OPT_FUSED, 2))
             b2 = rx.decode_batch(caps, baud_rate=bd, amp_end_threshold=th)
             assert np.array_equal(b.results, b2.results) and b.payloads() == b2.payloads()
             _assert_equals_oracle(b2, caps, bd, th)

@@ -381,6 +381,9 @@ class PipelinedRxSession:
         # any field view for as long as it likes while the staging set is reused by the next decode.
         self._stage = (_cabi.PinnedArray((max(self.B, 1),), _cabi.RX_RESULT_DTYPE),
                        _cabi.PinnedArray((max(int(self.blob_lo[-1]), 1),), np.uint8))
+        # GPUs that share a host link take turns copying (h2d_gate.py; None on boxes where every GPU has its own)
+        from .h2d_gate import make_gate
+        self.gate = make_gate(device)
         _cabi.stream_sync(device)          # plan set-up (default stream) is complete before the side streams run
 
     @staticmethod
@@ -401,7 +404,11 @@ class PipelinedRxSession:
         res, blob = (h.array for h in self._stage)
         for j, ((lo, hi), sess) in enumerate(zip(self.ranges, self.sessions)):
             a, b = int(self.offsets[lo]), int(self.offsets[hi])
-            if b > a:
+            if b > a and self.gate is not None:
+                with self.gate:            # the link is this GPU's for the length of the copy
+                    self.d_samples.upload(samples[a:b], self.copy_stream, offset=2 * a)
+                    _cabi.stream_sync(self.device, self.copy_stream)
+            elif b > a:
                 self.d_samples.upload(samples[a:b], self.copy_stream, offset=2 * a)
             _cabi.stream_wait_stream(self.device, self.compute_stream, self.copy_stream)
             sess.run(self.compute_stream)
@@ -425,6 +432,9 @@ class PipelinedRxSession:
         for h in getattr(self, "_stage", ()):
             h.close()
         self._stage = ()
+        if getattr(self, "gate", None) is not None:
+            self.gate.close()
+            self.gate = None
 
     __del__ = close
 

@@ -612,7 +612,9 @@ def run_e2e(args, state, all_samples):
            "api": "Receiver.decode_batch(pinned int16 samples, offsets, baud_rate=[...], amp_end_threshold=[...])",
            "h2d_overlapped_ranges": len(getattr(sess_e, "sessions", [None])),
            "steps": args.e2e_steps, "first_call_ms": first_ms, "h2d_only_ms": h2d_ms, "h2d_only_gbs": 2.0 * total / h2d_ms / 1e6,
-           "share_of_step_in_h2d": h2d_ms / e2e_ms}
+           "share_of_step_in_h2d": h2d_ms / e2e_ms,
+           "h2d_gate": (lambda g: None if g is None else f"{g.slots} GPUs of every group of {len(g._fds) and __import__('afskmodem_b200.h2d_gate', fromlist=['x']).default_policy(Ctx.ndev)[0]} copy at a time, taking turns range by range")(getattr(sess_e, "gate", None)),
+           "aggregate_h2d_gbs": 2.0 * all_samples / (e2e_ms / 1000) / 1e9}
     rx.close()
     extra = {}
     # ---- ONE corpus on all the GPUs of this job from ONE process (the product's multi-device call):

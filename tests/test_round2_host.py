@@ -145,3 +145,39 @@ def test_bench_corpus_is_seeded_by_capture_index():
         assert lens[i] == c.lead[i] + len(fr)
     w = bench.Corpus("c2", 8 * 64)
     assert w.payloads(64, 128) == bench.Corpus("c2", 8 * 64).payloads(0, 512)[64:128]
+
+
+def test_h2d_gate_serialises_a_group_only(tmp_path, monkeypatch):
+    """GPUs that share a host link take turns copying (h2d_gate.py): members of one group never hold the gate
+    together, members of different groups do; the policy follows AFSK_H2D_GATE and the number of visible GPUs."""
+    import threading
+    import time
+
+    from afskmodem_b200 import h2d_gate
+    inside, peak, lock = [0], [0], threading.Lock()
+
+    def work(dev):
+        g = h2d_gate.H2DGate(dev, 2, 1, root=str(tmp_path))
+        for _ in range(30):
+            with g:
+                with lock:
+                    inside[0] += 1
+                    peak[0] = max(peak[0], inside[0])
+                time.sleep(0.0005)
+                with lock:
+                    inside[0] -= 1
+        g.close()
+
+    for devs, want in (((0, 1), 1), ((0, 2), 2)):
+        peak[0] = 0
+        ts = [threading.Thread(target=work, args=(d,)) for d in devs]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert peak[0] <= want and (want == 1 or peak[0] >= 1)
+    monkeypatch.delenv("AFSK_H2D_GATE", raising=False)
+    assert h2d_gate.default_policy(1) is None and h2d_gate.default_policy(4) is None
+    assert h2d_gate.default_policy(8) == (4, 2)
+    monkeypatch.setenv("AFSK_H2D_GATE", "off")
+    assert h2d_gate.default_policy(8) is None
+    monkeypatch.setenv("AFSK_H2D_GATE", "4:2")
+    assert h2d_gate.default_policy(2) == (4, 2)

@@ -119,7 +119,7 @@ void parallel_for(int n, int threads, F &&body)
 // ---- pinned staging ring (process-wide, grow-only) --------------------------------------------------
 // afsk_wav_load with h_dst == NULL streams the files through a few pinned slots instead of pinning one
 // buffer as large as the corpus: the first call of a process then costs the same as every later one
-// (pinning 1.2 GB takes ~0.4 s; the ring is <= 192 MB and is kept), and the samples never need a second
+// (pinning 1.2 GB takes ~0.4 s; the ring is 32 MB by default and is kept), and the samples never need a second
 // host copy.  One ring-mode load runs at a time (mutex); slot j of a call is reused by span j + R only
 // after the H2D copy of span j has completed (event).
 struct StageRing {
@@ -162,11 +162,13 @@ int wav_load_ring(const char *const *paths, int n, int threads, const int64_t *h
     if (total <= 0) return AFSK_OK;
     if (span_samples <= 0) {
         const char *ev = getenv("AFSK_WAV_SLOT_MB");
-        span_samples = (int64_t)((ev && atoi(ev) > 0) ? atoi(ev) : 32) << 19;     // default 32 MB per slot
+        // default 8 MB per slot: measured on 1024 files / 1.23 GB from /dev/shm (tools/cold_sweep.py, fresh process
+        // each): 32 MB x 6 slots first call 129 ms / later 44 ms, 16 MB x 4: 72 / 30, 8 MB x 4: 55 / 29, 4 MB x 8: 57 / 29
+        span_samples = (int64_t)((ev && atoi(ev) > 0) ? atoi(ev) : 8) << 19;
     }
     span_samples = std::max<int64_t>(4096, std::min<int64_t>(span_samples, (total + 4095) & ~(int64_t)4095));
     const int nspans = (int)((total + span_samples - 1) / span_samples);
-    int R = 6;
+    int R = 4;
     if (const char *ev = getenv("AFSK_WAV_SLOTS")) R = std::max(2, std::min(StageRing::kMaxSlots, atoi(ev)));
     R = std::min(R, std::max(nspans, 1));
     std::vector<Piece> pieces;

@@ -103,7 +103,8 @@ struct DemodParams {
     int nv;           // 16-byte vectors each thread reads
     int nt;           // weight-table entries per (part, alignment): nv, or nv - 1 in merge mode
     int merge;        // seg % 8 == 0: head and tail partial vectors are merged into one
-    int wt;           // windows per tile = kConsumerThreads >> tpw_log2
+    int wt;           // windows per tile = nsub * (kConsumerThreads >> tpw_log2)
+    int nsub;         // sub-tiles per tile (general kernel; 1 elsewhere)
     int stage_bytes;
     int stages;
     int l2_hint;      // 1: bulk copies carry an L2 evict-first policy
@@ -786,6 +787,7 @@ __global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p
 
     // ---------------------------------------------------------------- consumers ----
     const int w = tid >> p.tpw_log2, part = tid & (tpw - 1);
+    const int wsub = kConsumerThreads >> p.tpw_log2;          // windows per sub-tile
     const int bf = p.bf, nv = p.nv;
     const int rel0 = w * bf + part * p.seg;
     const int two_bf = 2 * bf;
@@ -802,9 +804,15 @@ __global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
         if (p.fused_frame) signal_note(p, AS, sig, m.gpos, m.want, lane);
+        // a tile is nsub sub-tiles of kConsumerThreads >> tpw_log2 windows each: where a thread's segment is short
+        // (16 samples at 1500 / 750 / 375 baud, so that 128-bit loads are 2-way instead of 4-way bank conflicted) the
+        // tile still is 32 KB, which is what the copy engine wants (8 KB tiles: 4.7 TB/s, 32 KB: 6.7)
+#pragma unroll 1
+        for (int u = 0; u < p.nsub; u++) {
+        const int wbase = u * wsub;                            // first window of the sub-tile
         bool bit = false, quiet = false;
-        if (m.nwin > 0) {
-            const int rel = m.e0 + rel0;
+        if (m.nwin > wbase) {
+            const int rel = m.e0 + rel0 + wbase * bf;
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (rel >> 3);
             const uint4 *wp = wtab + part * PSq + (rel & 7) * ESq;
             int Um = 0, Nm = 0, Us = 0, Ns = 0, accA = 0;
@@ -930,17 +938,21 @@ __global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p
                     b1 = (S2 - M2 >= two_bf) || (M2 < (S2 / two_bf) * two_bf);   // floor(M/bf) < floor(S/bf)
                 }
             }
-            const bool valid = (part == 0) && (w < m.nwin);
+            const bool valid = (part == 0) && (wbase + w < m.nwin);
             bit = valid && b1;
             quiet = valid && (accA < m.thr_bf);                // getAmplitude(chunk) < amp_end :375
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);                   // stage may be refilled
-        if (m.nwin > 0) {
+        if (u == p.nsub - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);               // stage may be refilled
+        }
+        if (m.nwin > wbase) {
+            const long long word0 = m.word_base + (wbase >> 5);
+            const int nleft = m.nwin - wbase;                    // valid windows from this sub-tile on
             if (p.tpw_log2 == 0) {
                 const uint32_t bw = __ballot_sync(0xFFFFFFFFu, bit);
                 const uint32_t qw = __ballot_sync(0xFFFFFFFFu, quiet);
-                if (lane == 0 && warp * 32 < m.nwin) p.planes[m.word_base + warp] = make_uint2(bw, qw);
+                if (lane == 0 && warp * 32 < nleft) p.planes[word0 + warp] = make_uint2(bw, qw);
             } else if (p.tpw_log2 <= 2) {
                 // 2 or 4 threads per window: the part-0 lanes hold the decisions; squeeze the
                 // stride-tpw ballot into 16 / 8 bits and store them as a sub-word of the plane
@@ -949,8 +961,8 @@ __global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p
                 uint32_t qw = __ballot_sync(0xFFFFFFFFu, quiet);
                 const int per_warp = 32 >> p.tpw_log2;
                 const int w0 = warp * per_warp;
-                if (lane == 0 && (w0 & ~31) < m.nwin) {          // every piece of a word that holds a valid window
-                    uint8_t *dst = reinterpret_cast<uint8_t *>(p.planes + m.word_base + (w0 >> 5)) + ((w0 & 31) >> 3);
+                if (lane == 0 && (w0 & ~31) < nleft) {           // every piece of a word that holds a valid window
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(p.planes + word0 + (w0 >> 5)) + ((w0 & 31) >> 3);
                     if (p.tpw_log2 == 1) {
                         bw = squeeze2(bw); qw = squeeze2(qw);
                         *reinterpret_cast<uint16_t *>(dst) = (uint16_t)bw;
@@ -962,17 +974,18 @@ __global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p
                     }
                 }
             } else {
-                uint8_t *rb = resbuf + (n & 1) * kConsumerThreads;
+                uint8_t *rb = resbuf + ((n * p.nsub + u) & 1) * kConsumerThreads;
                 if (part == 0) rb[w] = (uint8_t)((bit ? 1 : 0) | (quiet ? 2 : 0));
                 asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
-                if (warp * 32 < p.wt) {
+                if (warp * 32 < wsub) {
                     const uint8_t r = rb[warp * 32 + lane];
                     const uint32_t bw = __ballot_sync(0xFFFFFFFFu, r & 1);
                     const uint32_t qw = __ballot_sync(0xFFFFFFFFu, r & 2);
-                    if (lane == 0 && warp * 32 < m.nwin) p.planes[m.word_base + warp] = make_uint2(bw, qw);
+                    if (lane == 0 && warp * 32 < nleft) p.planes[word0 + warp] = make_uint2(bw, qw);
                 }
             }
         }
+        }   // sub-tiles
         if (++s == S) { s = 0; ph ^= 1u; }
     }
     if (p.fused_frame) signal_finish(p, AS, sig, lane);
@@ -1866,7 +1879,7 @@ __global__ void __launch_bounds__(32) k_gate_multi(const int32_t *__restrict__ a
 }
 
 struct Group {
-    int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, stage_bytes = 0, stages = 0;
+    int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, nsub = 1, stage_bytes = 0, stages = 0;
     int small_wpt = 0;            // > 0: k_demod_lane<bf/8, small_wpt>
     int shift_wpt = 0;            // > 0: k_demod_shift<bf, shift_wpt>
     size_t smem = 0;
@@ -2019,12 +2032,22 @@ static bool configure_group(Group &g, int bf)
     // 32 is 4-way (75-89 % of it: 1500 / 750 / 375 baud).  Measured and rejected: segments of 64
     // samples in merge mode (8-way, 57 %) and two 32-sample windows per thread (83 %).
     while ((bf >> g.tpw_log2) > 48 && g.tpw_log2 < 3) g.tpw_log2++;
+    // Two sub-tiles per tile (three where a thread's segment is 32 samples): 40-48 KB tiles in a 2-stage ring
+    // instead of 16-24 KB tiles in a 3-stage ring.  Same box, alternating runs (gpurun_out/r2e, r2e2; GB/s of the
+    // demodulator): 1200 baud 6600 -> 6880, 300 baud 5820 -> 6130, 1000 baud 6786 -> 6935, 500 baud 6069 -> 6350,
+    // 800 baud 4533 -> 4765, 480 baud 3766 -> 3974, 400 baud 4398 -> 4603, 240 baud 3219 -> 3431; 1500 / 750 / 375 baud
+    // 5814 / 5031 / 4565 -> 5813 / 5371 / 4854 with three.  Three sub-tiles elsewhere cost a ring stage (c2: 5937).
+    // (Shorter segments with more threads per window, to halve the bank conflicts of 32-sample segments, lose far
+    // more in shuffles than they gain: 1500 baud 4124 GB/s.)
+    g.nsub = (bf == 32 || bf == 64 || bf == 128) ? 3 : 2;
+    if (const char *ev = getenv("AFSK_DEMOD_TPW_LOG2")) g.tpw_log2 = std::max(0, std::min(3, atoi(ev)));   // tuning runs
+    if (const char *ev = getenv("AFSK_DEMOD_NSUB")) g.nsub = std::max(1, std::min(8, atoi(ev)));
     const int tpw = 1 << g.tpw_log2;
     g.seg = (bf + tpw - 1) / tpw;
     g.nv = (g.seg + 6) / 8 + 1;
-    g.merge = (g.seg % 8 == 0 && g.seg <= 48) ? 1 : 0;   // then bf == tpw * seg and nv == seg/8 + 1
+    g.merge = (g.seg % 8 == 0 && g.seg <= 48 && bf % tpw == 0) ? 1 : 0;   // then bf == tpw * seg and nv == seg/8 + 1
     g.nt = g.merge ? g.nv - 1 : g.nv;
-    g.wt = kConsumerThreads / tpw;
+    g.wt = g.nsub * (kConsumerThreads / tpw);
     g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 256) + 127) & ~127;   // copy (e0 < 64) + over-read slack
     g.stages = pick_stages(g.stage_bytes);
     g.smem = demod_smem_bytes(g);
@@ -2441,7 +2464,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         p.gcaps = g.d_caps; p.gtile_first = g.d_tile_first; p.tile_gpos = g.d_tile_gpos;
         p.planes = P->d_planes;
         p.ng = (int)g.caps.size(); p.total_items = g.tile_first.back();
-        p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.nt = g.nt; p.merge = g.merge; p.wt = g.wt;
+        p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.nt = g.nt; p.merge = g.merge; p.wt = g.wt; p.nsub = g.nsub;
         p.stage_bytes = g.stage_bytes; p.stages = g.stages;
         // L2 evict-first on the bulk copies (the samples are read once).  Same-box A/B: k_demod +2-6 %
         // (c2 0.768 -> 0.745 ms, 600 baud 0.819 -> 0.770), k_demod_shift +1-2.5 %, the short-window kernel 0 to -10 %

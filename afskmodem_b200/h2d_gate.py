@@ -35,7 +35,7 @@ class H2DGate:
         root = root or ("/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp")
         d = os.path.join(root, f"afsk_h2d_gate_{os.getuid()}")
         os.makedirs(d, exist_ok=True)
-        self.group_id, self.member = device // group, device % group
+        self.group, self.group_id, self.member = group, device // group, device % group
         self.slots = min(slots, group)
         # one open file description per gate object: flock conflicts between descriptions, also inside a process
         self._fds = [os.open(os.path.join(d, f"g{self.group_id}_s{j}.lock"), os.O_RDWR | os.O_CREAT, 0o600)

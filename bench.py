@@ -613,7 +613,8 @@ def run_e2e(args, state, all_samples):
            "h2d_overlapped_ranges": len(getattr(sess_e, "sessions", [None])),
            "steps": args.e2e_steps, "first_call_ms": first_ms, "h2d_only_ms": h2d_ms, "h2d_only_gbs": 2.0 * total / h2d_ms / 1e6,
            "share_of_step_in_h2d": h2d_ms / e2e_ms,
-           "h2d_gate": (lambda g: None if g is None else f"{g.slots} GPUs of every group of {len(g._fds) and __import__('afskmodem_b200.h2d_gate', fromlist=['x']).default_policy(Ctx.ndev)[0]} copy at a time, taking turns range by range")(getattr(sess_e, "gate", None)),
+           "h2d_gate": (lambda g: None if g is None else f"{g.slots} of every {g.group} consecutive GPUs copy at a time, taking turns range by "
+                                                             "range (afskmodem_b200/h2d_gate.py)")(getattr(sess_e, "gate", None)),
            "aggregate_h2d_gbs": 2.0 * all_samples / (e2e_ms / 1000) / 1e9}
     rx.close()
     extra = {}
@@ -673,7 +674,7 @@ def run_e2e(args, state, all_samples):
             extra["e2e_files"] = {"value": res["ring"]["value"], "unit": "Msamples/s", "files": nf, "ms": res["ring"]["ms"],
                                   "first_call_ms": res["ring"]["first_call_ms"], "file_bytes": int(2 * offsets[nf] + 44 * nf),
                                   "where": tmpdir.rsplit("/", 1)[0], "api": "Receiver.load_batch(filenames, string=False)",
-                                  "host_threads": os.cpu_count(), "staging": "ring of pinned 32 MB slots (default)",
+                                  "host_threads": os.cpu_count(), "staging": "ring of four pinned 8 MB slots (default)",
                                   "pinned_corpus_mode": res["pinned_corpus"]}
             # cold: the first load_batch of a FRESH process (CUDA initialisation reported separately)
             try:

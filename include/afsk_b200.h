@@ -219,7 +219,7 @@ int afsk_wav_probe(const char *const *paths, int n, int threads, int64_t *h_nsam
  * spans of about span_samples consecutive samples are copied to d_dst (same offsets) on `stream` as
  * soon as their files are in memory, so that reading overlaps the PCIe transfer.
  * h_dst == NULL (d_dst required): the files stream through a process-wide ring of pinned staging slots
- * (span_samples each, 32 MB by default) straight to the device; no host copy of the corpus is kept, the
+ * (span_samples each, 8 MB by default, four slots) straight to the device; no host copy of the corpus is kept, the
  * first call of a process costs what later calls cost, and the call returns once every copy has landed. */
 int afsk_wav_load(const char *const *paths, int n, int threads, const int64_t *h_data_pos, const int64_t *h_nsamples,
                   const int64_t *h_offsets, int16_t *h_dst, int device, int16_t *d_dst, int64_t span_samples,

@@ -1099,10 +1099,14 @@ __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodPa
         mbar_wait(&full[s], ph);
         const TileMeta m = meta[s];
         if (p.fused_frame) signal_note(p, AS, sig, m.gpos, m.want, lane);
+#pragma unroll 1
+        for (int u = 0; u < p.nsub; u++) {           // sub-tiles of kConsumerThreads * kWpt windows (see k_demod)
+        const int wbase = u * kConsumerThreads * kWpt;
         uint32_t bits = 0, quiet = 0;
-        if (m.nwin > 0) {
-            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) + tid * (kSeg / 8);
-            const int nvalid = m.nwin - tid * kWpt;
+        if (m.nwin > wbase) {
+            const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) +
+                              (u * kConsumerThreads + tid) * (kSeg / 8);
+            const int nvalid = m.nwin - wbase - tid * kWpt;
             switch (m.e0 & 7) {                      // uniform over the CTA
             case 0: shift_decode<kBf, kWpt, 0>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
             case 1: shift_decode<kBf, kWpt, 1>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
@@ -1114,9 +1118,11 @@ __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodPa
             default: shift_decode<kBf, kWpt, 7>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-        if (m.nwin > 0) {
+        if (u == p.nsub - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (m.nwin > wbase) {
             // kLanesPerWord threads hold the kWpt-bit pieces of one plane word
             uint32_t bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
             uint32_t qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
@@ -1126,8 +1132,10 @@ __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodPa
                 qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
             }
             const int word = (tid * kWpt) >> 5;
-            if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin) p.planes[m.word_base + word] = make_uint2(bw, qw);
+            if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin - wbase)
+                p.planes[m.word_base + (wbase >> 5) + word] = make_uint2(bw, qw);
         }
+        }   // sub-tiles
         if (++s == S) { s = 0; ph ^= 1u; }
     }
     if (p.fused_frame) signal_finish(p, AS, sig, lane);
@@ -2006,6 +2014,8 @@ static bool configure_group(Group &g, int bf)
         // short windows: lane-major tiles of 256 * kJ windows (k_demod_lane<bf/8, kJ, 8 warps>), kJ = 8 / 4 / 2.  Smaller
         // tiles are slower (6000 baud, same box: 32 KB tiles 6661 GB/s, 16 KB 5756-6079, 8 KB 4715)
         g.small_wpt = bf == 8 ? 8 : (bf == 16 ? 4 : 2);
+        // (48 KB tiles in a two-stage ring, kJ = 12 / 6 / 3: 6000 baud 6570 -> 6485 GB/s, 3000 baud 6783 -> 6844, 2000 baud
+        // 6789 -> 6877 on one box: not worth the extra instantiations)
         g.seg = bf * g.small_wpt;
         g.nv = g.seg / 8 + 1;
         g.nt = g.nv; g.merge = 0;
@@ -2021,7 +2031,9 @@ static bool configure_group(Group &g, int bf)
         g.seg = bf * g.shift_wpt;
         g.nv = g.seg / 8 + 1;
         g.nt = g.nv; g.merge = 0;
-        g.wt = kConsumerThreads * g.shift_wpt;
+        g.nsub = 2;                          // two sub-tiles per tile: 4000 baud 5932 -> 6178 GB/s, 2400 baud 6006 -> 6397 (same box)
+        if (const char *ev = getenv("AFSK_DEMOD_NSUB")) g.nsub = std::max(1, std::min(8, atoi(ev)));
+        g.wt = g.nsub * kConsumerThreads * g.shift_wpt;
         g.stage_bytes = ((g.wt * bf * 2 + 16 + 256) + 127) & ~127;
         g.stages = pick_stages(g.stage_bytes);
         g.smem = demod_smem_bytes(g);
@@ -2047,13 +2059,17 @@ static bool configure_group(Group &g, int bf)
     g.nv = (g.seg + 6) / 8 + 1;
     g.merge = (g.seg % 8 == 0 && g.seg <= 48 && bf % tpw == 0) ? 1 : 0;   // then bf == tpw * seg and nv == seg/8 + 1
     g.nt = g.merge ? g.nv - 1 : g.nv;
-    g.wt = g.nsub * (kConsumerThreads / tpw);
-    g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 256) + 127) & ~127;   // copy (e0 < 64) + over-read slack
-    g.stages = pick_stages(g.stage_bytes);
-    g.smem = demod_smem_bytes(g);
-    while (g.smem > 113 * 1024 && g.stages > 2) {      // keep two CTAs per SM when the tables are large
-        g.stages--;
+    for (;; g.nsub--) {
+        g.wt = g.nsub * (kConsumerThreads / tpw);
+        g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 256) + 127) & ~127;   // copy (e0 < 64) + over-read slack
+        g.stages = pick_stages(g.stage_bytes);
         g.smem = demod_smem_bytes(g);
+        while (g.smem > 113 * 1024 && g.stages > 2) {      // keep two CTAs per SM when the tables are large
+            g.stages--;
+            g.smem = demod_smem_bytes(g);
+        }
+        // very long bits (below 100 baud): the sub-tiled ring would not leave two stages and two CTAs per SM
+        if (g.nsub == 1 || (g.smem <= 113 * 1024 && g.stages >= 2)) break;
     }
     while (g.smem > 227 * 1024 && g.stages > 1) {
         g.stages--;

@@ -461,6 +461,31 @@ __device__ uint32_t aux_clock_index(const int16_t *__restrict__ x, long long off
     return best & 4095u;                                         // first index of the minimum (:332-337)
 }
 
+// k_clock2: the auxiliary warps' clock job (aux_clock_index) as a kernel of its own, one 128-thread CTA per capture.
+// Against k_clock it needs 9.7 KB instead of 17 KB of shared memory and no 35-register array of candidate
+// distances (one sweep with the key minimum), so more captures are in flight per SM; bit lengths up to kAuxMaxBf.
+__global__ void __launch_bounds__(128, 12) k_clock2(const int16_t *__restrict__ x, const CapDesc *__restrict__ caps,
+                                                int32_t *__restrict__ clock, AfskRxResult *__restrict__ res)
+{
+    __shared__ AuxSmem S;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const CapDesc d = caps[c];
+    if (d.status0 != 0) {
+        if (tid == 0) {
+            clock[c] = -1;
+            AfskRxResult r;
+            r.status = d.status0; r.clock = -1; r.train_end = -1; r.nbits = 0; r.nbytes = 0;
+            res[c] = r;
+        }
+        return;
+    }
+    const uint32_t dv = 2u * (uint32_t)d.bf;
+    const int shift = 28 + (32 - __clz((int)(dv - 1u)));                 // 28 + ceil(log2 dv)
+    const uint32_t magic = (uint32_t)((((unsigned long long)1 << shift) + dv - 1) / dv);
+    const uint32_t clk = aux_clock_index<4>(x, d.off, d.bf, magic, shift, S, tid);
+    if (tid == 0) clock[c] = (int32_t)clk;
+}
+
 // consumer-side state of fused framing (see signal_flush, defined with the framing code below): a consumer
 // warp notes the capture of every tile it finishes, one tile per lane, and reports 32 of them at a time
 struct TileSignal {
@@ -1976,6 +2001,8 @@ struct AfskRxPlan {
     int64_t sum_samples = 0;      // over the captures decoded on the GPU
     bool can_fuse = false;        // every group fits the auxiliary warps (bit length, shared memory)
     int fused = -1;               // AFSK_OPT_FUSED: -1 automatic, 0 three kernels, 1 fused clocks, 2 fused clocks and framing
+    int clock_kernel = 1;         // AFSK_OPT_CLOCK_KERNEL: 1 k_clock, 2 k_clock2 (bit lengths up to kAuxMaxBf)
+    bool can_clock2 = false;
     int frame_kernel = 0;         // AFSK_OPT_FRAME_KERNEL: 0 automatic, 1 k_frame_warp, 2 k_frame<128,4,int>, 3 <512,8,int>, 4 <512,8,long long>
     int l2_hint = -1;             // AFSK_OPT_L2_HINT / AFSK_L2_HINT (read once per plan): -1 per-kernel default
     bool timing = false;
@@ -2230,6 +2257,8 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
         P->d_cready = reinterpret_cast<unsigned long long *>(P->arena + cready_off);
         P->d_planes = reinterpret_cast<uint2 *>(P->arena + planes_off);
         P->can_fuse = !P->groups.empty();
+        P->can_clock2 = true;
+        for (const Group &g : P->groups) if (g.bf > kAuxMaxBf) P->can_clock2 = false;
         for (size_t gi = 0; gi < P->groups.size(); gi++) {
             Group &g = P->groups[gi];
             g.d_caps = reinterpret_cast<int32_t *>(P->arena + goff[5 * gi]);
@@ -2321,6 +2350,8 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     if (ev) P->l2_hint = atoi(ev);
     ev = getenv("AFSK_FUSED");
     if (ev) P->fused = atoi(ev) < 0 ? -1 : std::min(atoi(ev), 2);
+    ev = getenv("AFSK_CLOCK_KERNEL");
+    if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) P->clock_kernel = atoi(ev);
     ev = getenv("AFSK_FRAME_KERNEL");
     if (ev && atoi(ev) >= 0 && atoi(ev) <= 4) P->frame_kernel = atoi(ev);
     const int rc = plan_build(P, B, h_start, h_len, h_baud, h_amp_end);
@@ -2371,6 +2402,10 @@ int afsk_rx_plan_set_option(AfskRxPlan *P, int option, int value)
         return AFSK_OK;
     case AFSK_OPT_L2_HINT:
         P->l2_hint = value < 0 ? -1 : (value ? 1 : 0);
+        return AFSK_OK;
+    case AFSK_OPT_CLOCK_KERNEL:
+        if (value != 1 && value != 2) { afsk_set_error("AFSK_OPT_CLOCK_KERNEL: 1 or 2"); return AFSK_E_ARG; }
+        P->clock_kernel = value;
         return AFSK_OK;
     case AFSK_OPT_FUSED:
         if (value > 2) { afsk_set_error("AFSK_OPT_FUSED: -1..2"); return AFSK_E_ARG; }
@@ -2471,6 +2506,8 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         P->epoch++;
         if (P->epoch == 0) P->epoch = 1;                 // tag 0 is what a fresh arena holds
         if (P->n_preset > 0) k_preset<<<(P->B + 255) / 256, 256, 0, st>>>(P->d_caps, P->d_clock, d_res, P->B);
+    } else if (P->clock_kernel == 2 && P->can_clock2) {
+        k_clock2<<<P->B, 128, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
     } else {
         k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
     }

@@ -188,44 +188,54 @@ __global__ void __launch_bounds__(kScanThreads) k_tx_nibscan(const uint8_t *__re
     }
 }
 
-// frame n of a capture with unequal tones, as the duplicated pair SoundOutput.__convertFrames emits
-__device__ __forceinline__ uint32_t var_frame_pair(long long n, const TxDesc &d, const uint8_t *__restrict__ pay,
-                                                   const int64_t *__restrict__ ns, long long &g)
+// Position of frame n (even) in the bit sequence of a capture with unequal tones: bit index b (training,
+// terminator and coded bits counted together; b >= total_bits: the 4800 zero frames :468) and the frame's
+// offset u inside that bit's tone.  One 64-bit division (training) or one binary search over the codeword
+// start table (coded bits) — done once per 64 frames by k_synth_var, which then walks bit by bit.
+__device__ __forceinline__ void var_locate(long long n, const TxDesc &d, const uint8_t *__restrict__ pay,
+                                           const int64_t *__restrict__ ns, long long &b, int &u)
 {
     const long long ml = d.ml, sl = d.bf;
     const long long T0 = (d.ts_bits >> 1) * (ml + sl);       // training cycles: mark, space  :457-458
     if (n < T0) {
-        const long long r = n % (ml + sl);
-        return r < ml ? tone_pair(1u, (int)r, d.bf) : tone_pair(0u, (int)(r - ml), d.bf);
+        const long long cyc = n / (ml + sl);
+        const long long r = n - cyc * (ml + sl);
+        b = 2 * cyc + (r >= ml ? 1 : 0);
+        u = (int)(r >= ml ? r - ml : r);
+        return;
     }
     long long t = n - T0;
-    if (t < ml) return tone_pair(1u, (int)t, d.bf);          // terminator: mark, space x3   :460-462
+    if (t < ml) { b = d.ts_bits; u = (int)t; return; }       // terminator: mark, space x3   :460-462
     t -= ml;
-    if (t < 3 * sl) return tone_pair(0u, (int)(t % sl), d.bf);
+    if (t < 3 * sl) { const long long k = t / sl; b = d.ts_bits + 1 + k; u = (int)(t - k * sl); return; }
     t -= 3 * sl;
     const long long G = 2 * d.pay_len;
-    if (G == 0 || t >= ns[G]) return 0u;                     // 4800 zero frames :468
-    if (g < 0) {                                             // last codeword starting at or before t
-        long long a = 0, b = G;
-        while (b - a > 1) {
-            const long long mid = (a + b) >> 1;
-            if (ns[mid] <= t) a = mid; else b = mid;
-        }
-        g = a;
+    if (G == 0 || t >= ns[G]) { b = d.total_bits; u = 0; return; }
+    long long lo = 0, hi = G;                                // last codeword starting at or before t
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (ns[mid] <= t) lo = mid; else hi = mid;
     }
-    while (ns[g + 1] <= t) g++;
-    long long u = t - ns[g];
-    const uint32_t byte = pay[d.pay_off + (g >> 1)];
-    const uint32_t cw = hamming74_encode((g & 1) ? (byte & 15u) : (byte >> 4));
-#pragma unroll
-    for (int r = 0; r < 7; r++) {
-        const uint32_t bit = (cw >> r) & 1u;
-        const long long L = bit ? ml : sl;
-        if (u < L) return tone_pair(bit, (int)u, d.bf);
-        u -= L;
+    long long rem = t - ns[lo];
+    const uint32_t byte = pay[d.pay_off + (lo >> 1)];
+    const uint32_t cw = hamming74_encode((lo & 1) ? (byte & 15u) : (byte >> 4));
+    int r = 0;
+    for (; r < 6; r++) {
+        const long long L = ((cw >> r) & 1u) ? ml : sl;
+        if (rem < L) break;
+        rem -= L;
     }
-    return 0u;                                               // unreachable: t < ns[g + 1]
+    b = d.ts_bits + 4 + 7 * lo + r;
+    u = (int)rem;
 }
+
+// Unequal tones: a lane synthesizes 64 consecutive frames (8 output vectors) — one var_locate, then a walk along
+// the bit sequence (both tone lengths are even, so a duplicated pair never straddles two bits) — into a
+// per-warp staging block in shared memory (XOR-swizzled: conflict-free both ways); the warp then writes its
+// 256 vectors as coalesced 128-bit stores.  (One binary search per output vector, 11 dependent global loads
+// each, made the first version run at 0.46 TB/s.)
+constexpr int kVarVecPerLane = 8;
+constexpr int kVarBlockVecs = 32 * kVarVecPerLane;           // 256 vectors = 2048 frames per warp step
 
 __global__ void __launch_bounds__(kSynthThreads) k_synth_var(const uint8_t *__restrict__ pay,
                                                              const TxDesc *__restrict__ descs,
@@ -233,20 +243,50 @@ __global__ void __launch_bounds__(kSynthThreads) k_synth_var(const uint8_t *__re
                                                              const int64_t *__restrict__ nib_start,
                                                              int16_t *__restrict__ out)
 {
+    __shared__ uint4 stage[kSynthThreads / 32][kVarBlockVecs];
     const long long chunk = blockIdx.x;
     const TxDesc d = descs[chunk_cap[chunk]];
     if (d.ml == d.bf) return;                                // equal tones: k_synth
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t *ns = nib_start + d.nib_off;
     const long long nvec_cap = (d.out_len + 7) >> 3;
     const long long v0 = (chunk - d.chunk_first) * kChunkVecs;
     const long long vend = min(v0 + (long long)kChunkVecs, nvec_cap);
     uint4 *dst = reinterpret_cast<uint4 *>(out + d.out_off);
-    for (long long vi = v0 + threadIdx.x; vi < vend; vi += kSynthThreads) {
-        long long g = -1;
-        uint32_t w[4];
+    uint4 *st = stage[warp];
+    for (long long vb = v0 + (long long)warp * kVarBlockVecs; vb < vend; vb += (long long)(kSynthThreads / 32) * kVarBlockVecs) {
+        const long long vl = vb + (long long)lane * kVarVecPerLane;      // this lane's first vector
+        if (vl < vend) {
+            long long b;
+            int u;
+            var_locate(8 * vl, d, pay, ns, b, u);
+            uint32_t sym = b < d.total_bits ? tx_bit(b, d, pay) : 2u;
+            int L = sym == 2u ? 0x7FFFFFFF : (sym ? d.ml : d.bf);
 #pragma unroll
-        for (int j = 0; j < 4; j++) w[j] = var_frame_pair(8 * vi + 2 * j, d, pay, ns, g);
-        dst[vi] = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int k = 0; k < kVarVecPerLane; k++) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    w[j] = tone_pair(sym, u, d.bf);
+                    u += 2;
+                    if (u >= L) {                            // next bit of the sequence (__getFrames :463-467 appends tone after tone)
+                        u -= L;
+                        b++;
+                        sym = b < d.total_bits ? tx_bit(b, d, pay) : 2u;
+                        L = sym == 2u ? 0x7FFFFFFF : (sym ? d.ml : d.bf);
+                    }
+                }
+                const int v = lane * kVarVecPerLane + k;
+                st[v ^ ((v >> 3) & 7)] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kVarVecPerLane; r++) {
+            const int v = 32 * r + lane;
+            if (vb + v < vend) dst[vb + v] = st[v ^ ((v >> 3) & 7)];
+        }
+        __syncwarp();
     }
 }
 

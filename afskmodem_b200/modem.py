@@ -1052,22 +1052,46 @@ class Transmitter:
     def _as_bytes(data) -> bytes:
         return data.encode("utf-8") if isinstance(data, str) else bytes(data)     # :473-474, :482-483
 
-    def encode_batch(self, payloads, device: int | None = None) -> TxBatch:
+    def encode_batch(self, payloads, device: int | None = None, _host=None) -> TxBatch:
         """Frames ``save`` would write for each payload (str or bytes), synthesized on the GPU."""
         s = TxSession([self._as_bytes(p) for p in payloads], self._baud, self._ts_cycles,
                       self._device if device is None else device)
         try:
             s.upload()
             s.run()
-            return s.download()
+            host = None
+            if _host is not None:
+                host = _host(int(s.out_off[-1]))
+            return s.download(host=host)
         finally:
             s.close()
+
+    def _pinned_frames(self, n: int) -> np.ndarray:
+        """grow-only pinned staging buffer for save_batch: the D2H copy runs at link speed and the first touch of
+        a fresh pageable array (a page fault per 4 KB) is not paid on every call"""
+        cur = getattr(self, "_pinned", None)
+        if cur is None or cur.array.size < n:
+            if cur is not None:
+                cur.close()
+            self._pinned = _cabi.PinnedArray((max(n + n // 8, 16),), np.int16)
+        return self._pinned.array[:n]
 
     def save_batch(self, payloads, filenames, threads: int = 0) -> None:
         """``save`` for many payloads: one synthesis on the GPU, files written by the library's host
         threads (byte-identical to the reference's wave output)."""
-        batch = self.encode_batch(payloads)
+        batch = self.encode_batch(payloads, _host=self._pinned_frames)
         write_wav_batch(filenames, batch.samples, batch.out_off[:-1], batch.out_len, threads)
+
+    def close(self):
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
+            self._pinned = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
     def save(self, data: str | bytes, filename: str):
         """Transmits the given data, saving the resulting audio to a .wav file — afskmodem.py:481-484."""

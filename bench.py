@@ -959,6 +959,14 @@ def main():
             "roofline": rec["roofline"], "cpu_baseline": rec["cpu_baseline"], "tx": tx,
             "workloads": workloads or None, "sharded": sharded, "latency": latency}
     line.update(extra)
+    bt = os.path.join(ROOT, "profiles", "r2_baud_sweep.json")
+    if os.path.exists(bt) and extras:
+        try:
+            tj = json.load(open(bt))
+            line["baud_table"] = {"source": "profiles/r2_baud_sweep.json (tools/baud_sweep.py on a B200, not this run)",
+                                  "demod_gbs_by_baud": {k: v["demod_gbs"] for k, v in tj["table"].items()}}
+        except Exception:  # noqa: BLE001
+            pass
     if args.scaling == "strong" and sharded:
         # the strong-scaling corpus as the line's own value
         line.update({"value": sharded["value"], "ms_per_step": sharded["ms_per_step"], "scaling": "strong",

@@ -123,6 +123,9 @@ int afsk_rx_plan_destroy(AfskRxPlan *plan);
                                    profiles/r2_tuning_log.md; both stay available and parity-tested).  Bit lengths over
                                    185 frames (below 260 baud) keep the three kernels; captures of more than 2^18 bit
                                    windows keep the separate framing kernel. */
+#define AFSK_OPT_CLOCK_KERNEL 4 /* clock recovery kernel of the three-kernel schedule: 1 k_clock (two sweeps over candidate
+                                   distances kept in registers), 2 k_clock2 (one sweep with an exact multiply-shift floor,
+                                   half the shared memory; bit lengths up to 185 frames, else k_clock) */
 int afsk_rx_plan_set_option(AfskRxPlan *plan, int option, int value);
 /* capacity offsets (bytes, B+1 entries, host memory owned by the plan) of the decoded output */
 int afsk_rx_plan_out_offsets(const AfskRxPlan *plan, const int64_t **h_out_off);

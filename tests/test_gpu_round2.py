@@ -379,3 +379,26 @@ def test_fused_long_capture_and_retargeted_plan():
     finally:
         os.environ.pop("AFSK_FUSED")
         rx.close()
+
+
+@pytest.mark.parametrize("baud", [6000, 1200, 300, 2400, 4000, 1500, 800])
+def test_clock_kernel_variant_2(baud):
+    """k_clock2 (AFSK_OPT_CLOCK_KERNEL = 2): the one-sweep clock search as a kernel of its own == k_clock == oracle."""
+    rng = np.random.default_rng([61, baud])
+    bf = 48000 // baud
+    caps = []
+    for i in range(40):
+        fr = O.tx_frames(rng.integers(0, 256, 12, dtype=np.uint8).tobytes(), baud, 0.2)
+        x = np.concatenate([np.zeros(int(rng.integers(0, 2 * bf + 40)), np.int16), fr]).astype(np.int32)
+        if i % 2:
+            x = x + np.round(rng.normal(0, float(rng.choice([4000, 15000, 30000])), len(x))).astype(np.int32)
+        caps.append(np.clip(x, -32768, 32767).astype(np.int16))
+    caps.append(np.zeros(3000, np.int16))
+    b = np.full(len(caps), baud, np.int32)
+    thr = np.full(len(caps), 14000, np.int32)
+    samples, offsets = A.modem._concat(caps)
+    s = A.RxSession(offsets, b, thr)
+    _cabi.check(_cabi.lib().afsk_rx_plan_set_option(s.plan, _cabi.OPT_CLOCK_KERNEL, 2))
+    s.upload(samples); s.run()
+    _assert_equals_oracle(s.download(), caps, b, thr)
+    s.close()

@@ -13,12 +13,9 @@ from __future__ import annotations
 import numpy as np
 
 # k_demod* throughput in GB/s of int16 samples by samples-per-bit (48000 / baud), B200, device-resident
-# (python bench.py --workload w<baud>; profiles/r2_baud_sweep.json).  Unknown bit lengths: DEMOD_GBS_DEFAULT.
+# (tools/baud_sweep.py; profiles/r2_baud_sweep.json).  Bit lengths that are not in the table: DEMOD_GBS_DEFAULT.
 DEMOD_GBS = {200: 3441, 160: 6318, 128: 4867, 120: 4785, 100: 3979, 96: 6726, 80: 6357, 64: 5590, 60: 4951, 48: 7052,
              40: 6999, 32: 6041, 24: 6814, 20: 6334, 16: 6750, 12: 6142, 8: 6530, 4: 1287}
-DEMOD_GBS_DEFAULT.
-DEMOD_GBS = {160: 6670, 96: 6840, 80: 6640, 48: 6980, 40: 6880, 24: 6820, 20: 6410, 16: 6730, 12: 6250, 8: 6300,
-             32: 5900, 64: 5440, 128: 4990, 60: 5090, 120: 4900, 100: 4000, 200: 3390, 4: 1260}
 DEMOD_GBS_DEFAULT = 5000.0
 PER_CAPTURE_NS = 8.0           # k_clock + k_frame_warp per capture (c2: 36 us / 4096, c3: 100 us / 16384)
 PCIE_GBS = 55.0                # pinned host -> device, one B200 on PCIe 5 x16

@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kSynthThreads) k_synth_var(const uint8_t *__re
                 for (int j = 0; j < 4; j++) {
                     w[j] = tone_pair(sym, u, d.bf);
                     u += 2;
-                    if (u >= L) {                            // next bit of the sequence (__getFrames :463-467 appends tone after tone)
-                        u -= L;
+                    while (u >= L) {                         // next bit of the sequence (__getFrames :463-467 appends tone after tone;
+                        u -= L;                              //  at 24000 baud the mark tone has no frames at all, :81-85)
                         b++;
                         sym = b < d.total_bits ? tx_bit(b, d, pay) : 2u;
                         L = sym == 2u ? 0x7FFFFFFF : (sym ? d.ml : d.bf);

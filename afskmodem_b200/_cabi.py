@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("AFSK_LIB_PATH") or os.path.join(_HERE, "libafsk_b200.
 AFSK_OK, AFSK_E_ARG, AFSK_E_CUDA, AFSK_E_BAUD, AFSK_E_UNSUPPORTED = 0, -1, -2, -3, -4
 ST_OK, ST_NO_CLOCK, ST_NO_DATA = 0, 1, 2
 ST_EXC_WAVELEN, ST_EXC_INDEX, ST_EXC_BAUD = -1, -2, -3
-OPT_FRAME_KERNEL, OPT_L2_HINT, OPT_FUSED, OPT_CLOCK_KERNEL = 1, 2, 3, 4
+OPT_FRAME_KERNEL, OPT_L2_HINT, OPT_FUSED, OPT_CLOCK_KERNEL, OPT_GROUP_STREAMS = 1, 2, 3, 4, 5
 
 # every symbol include/afsk_b200.h declares (tests check the library exports them all)
 SYMBOLS = [

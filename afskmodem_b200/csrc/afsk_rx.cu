@@ -2007,6 +2007,12 @@ struct AfskRxPlan {
     int l2_hint = -1;             // AFSK_OPT_L2_HINT / AFSK_L2_HINT (read once per plan): -1 per-kernel default
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    int timed_launches = 0;       // demodulator launches covered by timing_events
+    // one stream per baud group after the first: the groups' kernels are independent (disjoint captures), so the
+    // next group's CTAs fill the SMs as the previous group's drain instead of waiting for its last CTA
+    int group_streams = 1;        // AFSK_OPT_GROUP_STREAMS
+    std::vector<cudaStream_t> gstreams;
+    std::vector<cudaEvent_t> gevents;   // [0] fork, [i] join of group i
 };
 
 // shared-memory ring of two CTAs per SM (228 KB per SM, 1 KB reserved per CTA).  Measured in one
@@ -2350,6 +2356,8 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     if (ev) P->l2_hint = atoi(ev);
     ev = getenv("AFSK_FUSED");
     if (ev) P->fused = atoi(ev) < 0 ? -1 : std::min(atoi(ev), 2);
+    ev = getenv("AFSK_GROUP_STREAMS");
+    if (ev) P->group_streams = atoi(ev) ? 1 : 0;
     ev = getenv("AFSK_CLOCK_KERNEL");
     if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) P->clock_kernel = atoi(ev);
     ev = getenv("AFSK_FRAME_KERNEL");
@@ -2377,6 +2385,7 @@ int afsk_rx_plan_reset(AfskRxPlan *P, int B, const int64_t *h_start, const int64
     }
     for (auto &ev : P->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     P->timing_events.clear();
+    P->timed_launches = 0;
     const int rc = plan_build(P, B, h_start, h_len, h_baud, h_amp_end);
     if (rc != AFSK_OK) { P->B = 0; P->groups.clear(); }  // unusable until the next successful reset
     return rc;
@@ -2387,6 +2396,8 @@ int afsk_rx_plan_destroy(AfskRxPlan *P)
     if (!P) return AFSK_OK;
     AfskDeviceGuard guard(P->device);
     for (auto &ev : P->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (cudaStream_t gs : P->gstreams) cudaStreamDestroy(gs);
+    for (cudaEvent_t ge : P->gevents) cudaEventDestroy(ge);
     cudaFree(P->arena);
     delete P;
     return AFSK_OK;
@@ -2402,6 +2413,9 @@ int afsk_rx_plan_set_option(AfskRxPlan *P, int option, int value)
         return AFSK_OK;
     case AFSK_OPT_L2_HINT:
         P->l2_hint = value < 0 ? -1 : (value ? 1 : 0);
+        return AFSK_OK;
+    case AFSK_OPT_GROUP_STREAMS:
+        P->group_streams = value ? 1 : 0;
         return AFSK_OK;
     case AFSK_OPT_CLOCK_KERNEL:
         if (value != 1 && value != 2) { afsk_set_error("AFSK_OPT_CLOCK_KERNEL: 1 or 2"); return AFSK_E_ARG; }
@@ -2479,7 +2493,8 @@ int afsk_rx_plan_demod_time(AfskRxPlan *P, float *ms_total, int *launches)
     }
     P->timing_events.clear();
     *ms_total = total;
-    *launches = n;
+    *launches = P->timed_launches ? P->timed_launches : n;     // overlapped groups are timed as one span per decode
+    P->timed_launches = 0;
     return AFSK_OK;
 }
 
@@ -2511,7 +2526,28 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     } else {
         k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
     }
-    for (const Group &g : P->groups) {
+    const int ngroups = (int)P->groups.size();
+    const bool multi = P->group_streams != 0 && ngroups > 1;
+    if (multi) {
+        while ((int)P->gstreams.size() < ngroups - 1) {
+            cudaStream_t gs;
+            AFSK_CUDA(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+            P->gstreams.push_back(gs);
+        }
+        while ((int)P->gevents.size() < ngroups) {
+            cudaEvent_t ge;
+            AFSK_CUDA(cudaEventCreateWithFlags(&ge, cudaEventDisableTiming));
+            P->gevents.push_back(ge);
+        }
+    }
+    cudaEvent_t span0 = nullptr, span1 = nullptr;      // timing of the whole demodulation when the groups overlap
+    if (multi && P->timing && cudaEventCreate(&span0) == cudaSuccess && cudaEventCreate(&span1) == cudaSuccess)
+        cudaEventRecord(span0, st);
+    if (multi) AFSK_CUDA(cudaEventRecord(P->gevents[0], st));             // the clocks (and preset results) are in place
+    for (int gi = 0; gi < ngroups; gi++) {
+        const Group &g = P->groups[gi];
+        cudaStream_t gs = (multi && gi > 0) ? P->gstreams[gi - 1] : st;
+        if (multi && gi > 0) AFSK_CUDA(cudaStreamWaitEvent(gs, P->gevents[0], 0));
         DemodParams p;
         p.samples = d_samples; p.caps = P->d_caps; p.clock = P->d_clock;
         p.gcaps = g.d_caps; p.gtile_first = g.d_tile_first; p.tile_gpos = g.d_tile_gpos;
@@ -2532,18 +2568,27 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         const int block = !fused ? kDemodThreads : ((g.small_wpt || g.shift_wpt) ? kFusedThreads4 : kFusedThreads2);
         const size_t smem = fused ? g.smem_fused : g.smem;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
-            cudaEventRecord(e0, st);
-        if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8, 8><<<grid, block, smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4, 8><<<grid, block, smem, st>>>(p);
-        else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2, 8><<<grid, block, smem, st>>>(p);
-        else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<grid, block, smem, st>>>(p);
-        else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<grid, block, smem, st>>>(p);
-        else launch_demod(g.merge, g.nt, grid, block, smem, st, p);
+        if (!multi && P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+            cudaEventRecord(e0, gs);
+        if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8, 8><<<grid, block, smem, gs>>>(p);
+        else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4, 8><<<grid, block, smem, gs>>>(p);
+        else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2, 8><<<grid, block, smem, gs>>>(p);
+        else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<grid, block, smem, gs>>>(p);
+        else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<grid, block, smem, gs>>>(p);
+        else launch_demod(g.merge, g.nt, grid, block, smem, gs, p);
         if (e0 && e1) {
-            cudaEventRecord(e1, st);
+            cudaEventRecord(e1, gs);
             P->timing_events.emplace_back(e0, e1);
         }
+        if (P->timing) P->timed_launches++;
+        if (multi && gi > 0) {
+            AFSK_CUDA(cudaEventRecord(P->gevents[gi], gs));
+            AFSK_CUDA(cudaStreamWaitEvent(st, P->gevents[gi], 0));         // join: framing needs every group's planes
+        }
+    }
+    if (span0 && span1) {
+        cudaEventRecord(span1, st);
+        P->timing_events.emplace_back(span0, span1);
     }
     if (fused_frame) {
         AFSK_CUDA(cudaGetLastError());

@@ -126,6 +126,9 @@ int afsk_rx_plan_destroy(AfskRxPlan *plan);
 #define AFSK_OPT_CLOCK_KERNEL 4 /* clock recovery kernel of the three-kernel schedule: 1 k_clock (two sweeps over candidate
                                    distances kept in registers), 2 k_clock2 (one sweep with an exact multiply-shift floor,
                                    half the shared memory; bit lengths up to 185 frames, else k_clock) */
+#define AFSK_OPT_GROUP_STREAMS 5 /* 1 (default): the demodulator launches of a mixed-baud batch (one per bit length) run on
+                                   streams of their own between the clock and framing kernels, so that one group's CTAs
+                                   fill the SMs as the previous group's drain; 0: one after the other on the caller's stream */
 int afsk_rx_plan_set_option(AfskRxPlan *plan, int option, int value);
 /* capacity offsets (bytes, B+1 entries, host memory owned by the plan) of the decoded output */
 int afsk_rx_plan_out_offsets(const AfskRxPlan *plan, const int64_t **h_out_off);

@@ -1051,8 +1051,13 @@ __device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int
 #pragma unroll
     for (int w = 0; w < kWpt; w++) {
         int accM = 0, accS = 0, accA = 0;
+        int UmF = 0, UsF = 0, NmF = 0, NsF = 0;      // windows of more than 120 samples: the packed sums are unpacked half way
 #pragma unroll
         for (int b = 0; b < kBf / 4; b++) {
+            if (kBf > 120 && b == kBf / 8) {
+                unpack_acc(accM, UmF, NmF); unpack_acc(accS, UsF, NsF);
+                accM = 0; accS = 0;
+            }
             const int pos = kE + w * kBf + 4 * b;    // first sample of the group in the loaded words
             uint32_t a0, a1;
             if ((kE & 1) == 0) {
@@ -1063,12 +1068,13 @@ __device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int
             }
             accum4_full(a0, a1, tone_weights4(kBf, 4 * b, false), tone_weights4(kBf, 4 * b, true), k512, accM, accS, accA);
         }
-        // acc = 256 * T.n + T.c with |T.c| <= kBf <= 127: decide as in k_demod
-        const int Um = (int)((unsigned)accM << 24) >> 24, Us = (int)((unsigned)accS << 24) >> 24;
+        // acc = 256 * T.n + T.c with |T.c| <= 127 (per half for long windows): decide as in k_demod
+        const int Um = UmF + ((int)((unsigned)accM << 24) >> 24), Us = UsF + ((int)((unsigned)accS << 24) >> 24);
         const int du = Um - Us;
         bool b1 = du > 0;
         if (du == 0) {
-            const int Nm = (accM - Um) >> 8, Ns = (accS - Us) >> 8;
+            const int Nm = NmF + ((accM - ((int)((unsigned)accM << 24) >> 24)) >> 8);
+            const int Ns = NsF + ((accS - ((int)((unsigned)accS << 24) >> 24)) >> 8);
             if (Ns > Nm) {
                 const int M2 = 65535 * kBf - 65534 * Um + 2 * Nm;
                 const int S2 = M2 + 2 * (Ns - Nm);
@@ -1936,11 +1942,16 @@ struct Group {
     X(1, true) X(2, true) X(3, true) X(4, true) X(5, true) X(6, true) \
     X(2, false) X(3, false) X(4, false) X(5, false) X(6, false) X(7, false) X(0, false)
 
+// k_demod_shift instantiations: (bit length, windows per thread)
+#define AFSK_SHIFT_VARIANTS(X) X(12, 4) X(20, 2) X(60, 2) X(100, 2) X(120, 1) X(200, 1)
+
 static cudaError_t demod_set_smem_attr()
 {
     cudaError_t e = cudaFuncSetAttribute(k_demod_lane<1, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#define X(BF, W) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<BF, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    AFSK_SHIFT_VARIANTS(X)
+#undef X
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<2, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<3, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 #define X(NT, MG) \
@@ -1967,8 +1978,10 @@ static const void *demod_kernel_of(const Group &g)
     if (g.small_wpt && g.bf == 8) return (const void *)k_demod_lane<1, 8, 8>;
     if (g.small_wpt && g.bf == 16) return (const void *)k_demod_lane<2, 4, 8>;
     if (g.small_wpt && g.bf == 24) return (const void *)k_demod_lane<3, 2, 8>;
-    if (g.shift_wpt && g.bf == 12) return (const void *)k_demod_shift<12, 4>;
-    if (g.shift_wpt && g.bf == 20) return (const void *)k_demod_shift<20, 2>;
+#define X(BF, W) \
+    if (g.shift_wpt == (W) && g.bf == (BF)) return (const void *)k_demod_shift<BF, W>;
+    AFSK_SHIFT_VARIANTS(X)
+#undef X
 #define X(NT, MG) \
     if ((MG) == (g.merge != 0) && (NT) == g.nt) return (const void *)k_demod<NT, MG>;
     AFSK_DEMOD_VARIANTS(X)
@@ -2058,17 +2071,26 @@ static bool configure_group(Group &g, int bf)
         g.smem = demod_smem_bytes(g);
         return true;
     }
-    if (bf == 12 || bf == 20) {
-        // windows of 4 (mod 8) samples: k_demod_shift, 2 or 4 windows per thread
-        g.shift_wpt = bf == 12 ? 4 : 2;      // measured at 4000 baud: 4 windows per thread 6245 GB/s, 2 -> 5366
+    // 800 / 480 / 400 / 240 baud (60 / 100 / 120 / 200 samples per bit): in the general kernel a thread's segment is not a whole
+    // number of vectors there (masked head / tail vectors, weight table in shared memory: 4.8 / 4.0 / 4.6 / 3.4 TB/s);
+    // k_demod_shift with 2 / 2 / 1 / 1 windows per thread reads 15 or 25 whole vectors per thread, conflict-free (odd
+    // multiples of 16 bytes between threads): 6.8 / 7.0 / 7.0 / 6.9 TB/s.  (The same kernel at 1200 / 1000 / 500 baud:
+    // 5.6 TB/s against 6.9 / 6.9 / 6.5 of the general kernel; at 600 / 300 baud within 1 %: they stay where they are.)
+    const bool long_shift = (bf == 60 || bf == 100 || bf == 120 || bf == 200) && !getenv("AFSK_NO_LONG_SHIFT");
+    if (bf == 12 || bf == 20 || long_shift) {
+        // windows whose thread segment is not a whole number of vectors in the general kernel: k_demod_shift with as many
+        // windows per thread as make it one (4000 / 2400 baud: 4 / 2 windows; 800 / 480 baud: 2; 400 / 240 baud: 1 window of
+        // 15 / 25 vectors).  The long ones are 60-100 KB per tile: one CTA per SM with a 2-3 stage ring.
+        g.shift_wpt = bf == 12 ? 4 : ((bf == 20 || bf == 60 || bf == 100) ? 2 : 1);   // measured at 4000 baud: 4 windows per thread 6245 GB/s, 2 -> 5366
         g.seg = bf * g.shift_wpt;
         g.nv = g.seg / 8 + 1;
         g.nt = g.nv; g.merge = 0;
-        g.nsub = 2;                          // two sub-tiles per tile: 4000 baud 5932 -> 6178 GB/s, 2400 baud 6006 -> 6397 (same box)
+        g.nsub = long_shift ? 1 : 2;         // two sub-tiles per tile: 4000 baud 5932 -> 6178 GB/s, 2400 baud 6006 -> 6397 (same box)
         if (const char *ev = getenv("AFSK_DEMOD_NSUB")) g.nsub = std::max(1, std::min(8, atoi(ev)));
         g.wt = g.nsub * kConsumerThreads * g.shift_wpt;
         g.stage_bytes = ((g.wt * bf * 2 + 16 + 256) + 127) & ~127;
         g.stages = pick_stages(g.stage_bytes);
+        if (long_shift) g.stages = (int)std::min<size_t>(3, (size_t)(220 * 1024) / (size_t)g.stage_bytes);
         g.smem = demod_smem_bytes(g);
         return true;
     }
@@ -2092,6 +2114,8 @@ static bool configure_group(Group &g, int bf)
     g.nv = (g.seg + 6) / 8 + 1;
     g.merge = (g.seg % 8 == 0 && g.seg <= 48 && bf % tpw == 0) ? 1 : 0;   // then bf == tpw * seg and nv == seg/8 + 1
     g.nt = g.merge ? g.nv - 1 : g.nv;
+    // (one CTA per SM with 60-80 KB tiles, which is what suits k_demod_shift's long per-thread segments, loses here:
+    //  1200 baud 5980 GB/s, 300 baud 4970, 600 baud 5250)
     for (;; g.nsub--) {
         g.wt = g.nsub * (kConsumerThreads / tpw);
         g.stage_bytes = ((g.wt * bf * 2 + g.nv * 16 + 2 * tpw + 256) + 127) & ~127;   // copy (e0 < 64) + over-read slack
@@ -2573,8 +2597,10 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         if (g.small_wpt && g.bf == 8) k_demod_lane<1, 8, 8><<<grid, block, smem, gs>>>(p);
         else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4, 8><<<grid, block, smem, gs>>>(p);
         else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2, 8><<<grid, block, smem, gs>>>(p);
-        else if (g.shift_wpt && g.bf == 12) k_demod_shift<12, 4><<<grid, block, smem, gs>>>(p);
-        else if (g.shift_wpt && g.bf == 20) k_demod_shift<20, 2><<<grid, block, smem, gs>>>(p);
+#define X(BF, W) \
+        else if (g.shift_wpt == (W) && g.bf == (BF)) k_demod_shift<BF, W><<<grid, block, smem, gs>>>(p);
+        AFSK_SHIFT_VARIANTS(X)
+#undef X
         else launch_demod(g.merge, g.nt, grid, block, smem, gs, p);
         if (e0 && e1) {
             cudaEventRecord(e1, gs);

@@ -105,6 +105,7 @@ struct DemodParams {
     int merge;        // seg % 8 == 0: head and tail partial vectors are merged into one
     int wt;           // windows per tile = nsub * (kConsumerThreads >> tpw_log2)
     int nsub;         // sub-tiles per tile (general kernel; 1 elsewhere)
+    int rot;          // 32-sample segments: rotated vector order (AFSK_NO_ROT=1 turns it off for A/B runs)
     int stage_bytes;
     int stages;
     int l2_hint;      // 1: bulk copies carry an L2 evict-first policy
@@ -823,6 +824,8 @@ __global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p
     uint32_t Dw[kNT > 0 ? kNT : 1][2], selA = 0, selB = 0;
     int cur_al = -1;
     const bool v0_quarter03 = kMerge && kNT >= 4 && p.tpw_log2 == 0;
+    constexpr bool kRot = kMerge && kNT == 4;                 // only 32-sample segments have four whole vectors
+    const int rot = (kRot && p.rot) ? ((tid >> 1) & 3) : 0;
     int s = 0;
     uint32_t ph = 0;
     for (int n = 0; n < ntile; ++n) {
@@ -846,18 +849,39 @@ __global__ void __launch_bounds__(kFusedThreads2, 2) k_demod(const DemodParams p
                 // ---- fast path: one packed accumulator of D = (mark - space) / 2 ----
                 // bf % 8 == 0 here, so every window of the tile has the alignment m.e0 & 7 and a thread's
                 // weights change only when the capture does: they are cached in registers
+                // kRot (32-sample segments, 64 bytes between threads: a 128-bit load of the same vector index by a quarter
+                // warp is a 4-way bank conflict): thread t takes its four vectors in the order (i + (t >> 1)) & 3, which
+                // spreads the eight threads over all banks.  The sums do not care about the order; the weights are cached
+                // in the same rotated order, and the head / tail merge of logical vector 0 becomes a PRMT with identity
+                // selectors for the other three.
                 if ((m.e0 & 7) != cur_al) {
                     cur_al = m.e0 & 7;
 #pragma unroll
                     for (int i = 0; i < kNT; i++) {
-                        const uint4 av = wp[2 * i + 1];
+                        const int li = kRot ? ((i + rot) & 3) : i;      // rot == 0 when the rotation is switched off
+                        const uint4 av = wp[2 * li + 1];
                         Dw[i][0] = av.x; Dw[i][1] = av.y;
-                        if (i == 0) { selA = av.z; selB = av.w; }
                     }
+                    const uint4 a0 = wp[1];
+                    selA = a0.z; selB = a0.w;
                 }
                 int accD = 0;
 #pragma unroll
                 for (int i = 0; i < kNT; i++) {
+                    if (kRot && p.rot) {
+                        const int li = (i + rot) & 3;
+                        const bool head = li == 0;
+                        uint4 dv = dp[li];
+                        const uint4 tv = head ? dp[kNT] : dv;      // tail vector: slots below e (logical vector 0 only)
+                        const uint32_t sA = head ? selA : 0x32103210u, sB = head ? selB : 0x32103210u;
+                        dv.x = prmt(dv.x, tv.x, sA);
+                        dv.y = prmt(dv.y, tv.y, sA >> 16);
+                        dv.z = prmt(dv.z, tv.z, sB);
+                        dv.w = prmt(dv.w, tv.w, sB >> 16);
+                        accum4_d(dv.x, dv.y, Dw[i][0], k512, accD, accA);
+                        accum4_d(dv.z, dv.w, Dw[i][1], k512, accD, accA);
+                        continue;
+                    }
                     uint4 dv = dp[i];
                     if (i == 0) {
                         const uint4 tv = dp[kNT];                  // tail vector: slots below e
@@ -2023,6 +2047,7 @@ struct AfskRxPlan {
     int timed_launches = 0;       // demodulator launches covered by timing_events
     // one stream per baud group after the first: the groups' kernels are independent (disjoint captures), so the
     // next group's CTAs fill the SMs as the previous group's drain instead of waiting for its last CTA
+    int rot = 1;                  // rotated vector order at 32-sample segments (tuning switch AFSK_NO_ROT)
     int group_streams = 1;        // AFSK_OPT_GROUP_STREAMS
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> gevents;   // [0] fork, [i] join of group i
@@ -2380,6 +2405,7 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     if (ev) P->l2_hint = atoi(ev);
     ev = getenv("AFSK_FUSED");
     if (ev) P->fused = atoi(ev) < 0 ? -1 : std::min(atoi(ev), 2);
+    if (getenv("AFSK_NO_ROT")) P->rot = 0;
     ev = getenv("AFSK_GROUP_STREAMS");
     if (ev) P->group_streams = atoi(ev) ? 1 : 0;
     ev = getenv("AFSK_CLOCK_KERNEL");
@@ -2578,6 +2604,9 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         p.planes = P->d_planes;
         p.ng = (int)g.caps.size(); p.total_items = g.tile_first.back();
         p.bf = g.bf; p.tpw_log2 = g.tpw_log2; p.seg = g.seg; p.nv = g.nv; p.nt = g.nt; p.merge = g.merge; p.wt = g.wt; p.nsub = g.nsub;
+        // rotated vector order: 375 baud 4357 -> 4800 GB/s, 750 baud 4730 -> 4855; at 1500 baud (one thread per window) it loses
+        // the amplitude-only treatment of the merged vector and with it 6 % (5690 -> 5340): off there
+        p.rot = (P->rot && g.tpw_log2 >= 1) ? 1 : 0;
         p.stage_bytes = g.stage_bytes; p.stages = g.stages;
         // L2 evict-first on the bulk copies (the samples are read once).  Same-box A/B: k_demod +2-6 %
         // (c2 0.768 -> 0.745 ms, 600 baud 0.819 -> 0.770), k_demod_shift +1-2.5 %, the short-window kernel 0 to -10 %

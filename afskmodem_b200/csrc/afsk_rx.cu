@@ -1967,7 +1967,7 @@ struct Group {
     X(2, false) X(3, false) X(4, false) X(5, false) X(6, false) X(7, false) X(0, false)
 
 // k_demod_shift instantiations: (bit length, windows per thread)
-#define AFSK_SHIFT_VARIANTS(X) X(12, 4) X(20, 2) X(60, 2) X(100, 2) X(120, 1) X(200, 1)
+#define AFSK_SHIFT_VARIANTS(X) X(4, 8) X(12, 4) X(20, 2) X(60, 2) X(100, 2) X(120, 1) X(200, 1)
 
 static cudaError_t demod_set_smem_attr()
 {
@@ -2102,11 +2102,11 @@ static bool configure_group(Group &g, int bf)
     // multiples of 16 bytes between threads): 6.8 / 7.0 / 7.0 / 6.9 TB/s.  (The same kernel at 1200 / 1000 / 500 baud:
     // 5.6 TB/s against 6.9 / 6.9 / 6.5 of the general kernel; at 600 / 300 baud within 1 %: they stay where they are.)
     const bool long_shift = (bf == 60 || bf == 100 || bf == 120 || bf == 200) && !getenv("AFSK_NO_LONG_SHIFT");
-    if (bf == 12 || bf == 20 || long_shift) {
+    if (bf == 4 || bf == 12 || bf == 20 || long_shift) {
         // windows whose thread segment is not a whole number of vectors in the general kernel: k_demod_shift with as many
         // windows per thread as make it one (4000 / 2400 baud: 4 / 2 windows; 800 / 480 baud: 2; 400 / 240 baud: 1 window of
         // 15 / 25 vectors).  The long ones are 60-100 KB per tile: one CTA per SM with a 2-3 stage ring.
-        g.shift_wpt = bf == 12 ? 4 : ((bf == 20 || bf == 60 || bf == 100) ? 2 : 1);   // measured at 4000 baud: 4 windows per thread 6245 GB/s, 2 -> 5366
+        g.shift_wpt = bf == 4 ? 8 : (bf == 12 ? 4 : ((bf == 20 || bf == 60 || bf == 100) ? 2 : 1));   // 12000 baud: eight 4-sample windows per thread   // measured at 4000 baud: 4 windows per thread 6245 GB/s, 2 -> 5366
         g.seg = bf * g.shift_wpt;
         g.nv = g.seg / 8 + 1;
         g.nt = g.nv; g.merge = 0;

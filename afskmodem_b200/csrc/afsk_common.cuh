@@ -135,6 +135,22 @@ __device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32
                  "l"(src), "r"(bytes), "r"(afsk_smem_u32(bar)), "l"(pol)
                  : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS.BYPASS): the destination is the thread's choice, which is what a
+// padded (bank-conflict-free) layout needs and a bulk copy cannot give
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void *src, uint64_t pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+// one arrival on the mbarrier once every cp.async this thread has issued so far has landed (the count is not raised:
+// the barrier's expected arrivals include it)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(afsk_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ uint4 ld_nc_v4(const void *p)
 {
     uint4 r;

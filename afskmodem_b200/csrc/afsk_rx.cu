@@ -109,6 +109,7 @@ struct DemodParams {
     int stage_bytes;
     int stages;
     int l2_hint;      // 1: bulk copies carry an L2 evict-first policy
+    int pad_warps;    // padded layout: warps that share the cp.async copies of a tile (1..5)
     // ---- fused mode: auxiliary warps of every CTA recover the clocks and frame the captures of this group
     //      inside the same launch (k_clock / k_frame_warp become jobs hidden under the HBM stream)
     int fused;        // 0: clocks come from k_clock (p.clock); 1: from the auxiliary warps (p.cready)
@@ -136,10 +137,11 @@ __device__ __forceinline__ long long num_windows(long long n, int bf, int clk)
 __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restrict__ x,
                                                          const CapDesc *__restrict__ caps,
                                                          int32_t *__restrict__ clock,
-                                                         AfskRxResult *__restrict__ res)
+                                                         AfskRxResult *__restrict__ res, uint32_t qmask)
 {
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const CapDesc d = caps[c];
+    if (d.status0 == 0 && (d.bf & 3) == 0 && d.bf <= 24 && ((qmask >> (d.bf >> 2)) & 1u)) return;   // k_clock_q's capture
     if (d.status0 != 0) {
         if (tid == 0) {
             clock[c] = -1;
@@ -287,6 +289,102 @@ __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restri
     if (tid == 0) {
         for (int w = 1; w < kClockThreads / 32; w++) first = min(first, warp_min[w]);
         clock[c] = (int32_t)first;
+    }
+}
+
+// ---------------------------------------------------------------------------- k_clock_q ----
+// __recoverClockIndex (:322-339) for the short bits (bf = 4 Q, Q = 2..6: 6000 / 4000 / 3000 / 2400 / 2000 baud), where a
+// batch holds the most captures per sample and k_clock's ~26 thread instructions per candidate show in the step.
+// No prefix array, no shared memory, no shuffles: thread t scores the 32 candidates at positions 32 b .. 32 b + 31 of
+// the 16-byte aligned sample stream y (b = the thread's block) from 4 + Q vectors it loads itself, all in registers:
+//     a[j] = y[j] + ... + y[j + Q - 1]                      (IDP.2A with +/-1 byte selectors; sliding from Q = 4)
+//     e[j] = a[j] - a[j + Q],   b[j] = a[j] + a[j + Q]
+//     D_j  = c0 - (e[j] + e[j + 2Q]) - (b[j + 4Q] - b[j + 6Q])        sum |training cycle - y[j ..]|, c0 = 65535 bf
+// (mark = +Q -Q +Q -Q, space = +2Q -2Q at full scale: |T - y| = 32767 - y or y + 32768), about 10 instructions per
+// candidate.  getDiff = floor(D / 2bf) (:107) by one exact multiply-high (D < 2^22), and the first minimum (:332-337)
+// is the minimum of the key (getDiff << 12) | position.  Candidate i sits at position i + e (e = capture start
+// modulo 8 samples); positions outside [e, e + span) are masked.  They all lie in blocks 0, 126 and 127, which the
+// block rotation b = (t + 126) & 127 puts into warp 0: the other three warps run the unmasked body.
+template <int kQ>
+__device__ __forceinline__ int clockq_sum(const uint32_t (&W)[16 + 4 * kQ], int j)
+{
+    // y[j] + ... + y[j + kQ - 1] straight from the words (samples 2k, 2k + 1 in W[k])
+    int acc = 0;
+#pragma unroll
+    for (int k = j >> 1; k <= (j + kQ - 1) >> 1; k++) {
+        const bool lo = 2 * k >= j, hi = 2 * k + 1 <= j + kQ - 1;
+        acc = __dp2a_lo((int)W[k], (lo ? 0x0001 : 0) | (hi ? 0x0100 : 0), acc);
+    }
+    return acc;
+}
+
+template <int kQ, bool kMasked>
+__device__ __forceinline__ uint32_t clockq_scan(const uint4 *__restrict__ src, int blk, int e, int span)
+{
+    constexpr int kNV = 4 + kQ, kNA = 32 + 7 * kQ, kNE = 32 + 2 * kQ;
+    constexpr uint32_t kDiv = 8u * kQ;                                   // 2 bf
+    constexpr uint32_t kMagic = (uint32_t)((0x100000000ull + kDiv - 1) / kDiv);   // floor(D / kDiv) == umulhi(D, kMagic), D < 2^22
+    uint32_t W[4 * kNV];
+#pragma unroll
+    for (int r = 0; r < kNV; r++) {
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        const int v = 4 * blk + r;
+        // the capture holds y[e, e + 4096): vectors 0..511, and vector 512 when its start is not aligned
+        if (!kMasked || v < 512 || (v == 512 && e > 0)) q = ld_nc_v4(src + v);
+        W[4 * r] = q.x; W[4 * r + 1] = q.y; W[4 * r + 2] = q.z; W[4 * r + 3] = q.w;
+    }
+    int a[kNA];
+    if (kQ <= 3) {
+#pragma unroll
+        for (int j = 0; j < kNA; j++) a[j] = clockq_sum<kQ>(W, j);
+    } else {
+        a[0] = clockq_sum<kQ>(W, 0);
+#pragma unroll
+        for (int j = 0; j + 1 < kNA; j++) {
+            const int t = __dp2a_lo((int)W[j >> 1], (j & 1) ? 0xFF00 : 0x00FF, a[j]);            // - y[j]
+            a[j + 1] = __dp2a_lo((int)W[(j + kQ) >> 1], ((j + kQ) & 1) ? 0x0100 : 0x0001, t);   // + y[j + Q]
+        }
+    }
+    int ee[kNE], bb[kNE];
+#pragma unroll
+    for (int j = 0; j < kNE; j++) {
+        ee[j] = a[j] - a[j + kQ];
+        bb[j] = a[j + 4 * kQ] + a[j + 5 * kQ];
+    }
+    const int c0 = 65535 * 4 * kQ;
+    const int lo = e - 32 * blk, hi = e + span - 32 * blk;              // valid positions of the block: lo <= k < hi
+    uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const int f = c0 - bb[k] + bb[k + 2 * kQ];
+        const uint32_t D = (uint32_t)(f - ee[k] - ee[k + 2 * kQ]);
+        uint32_t key = __umulhi(D, kMagic) * 4096u + (uint32_t)(32 * blk + k);
+        if (kMasked && (k < lo || k >= hi)) key = 0xFFFFFFFFu;
+        best = min(best, key);
+    }
+    return best;
+}
+
+template <int kQ>
+__global__ void __launch_bounds__(kClockThreads) k_clock_q(const int16_t *__restrict__ x, const CapDesc *__restrict__ caps,
+                                                           const int32_t *__restrict__ gcaps, int32_t *__restrict__ clock)
+{
+    const int c = gcaps[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t off = caps[c].off;
+    const int64_t ga = off & ~(int64_t)7;
+    const int e = (int)(off - ga);
+    const uint4 *src = reinterpret_cast<const uint4 *>(x + ga);
+    const int span = AFSK_SYNC_FRAMES - 8 * kQ;                          // :327
+    const int blk = (tid + 126) & 127;
+    __shared__ uint32_t warp_min[kClockThreads / 32];
+    uint32_t best = warp == 0 ? clockq_scan<kQ, true>(src, blk, e, span) : clockq_scan<kQ, false>(src, blk, e, span);
+    best = __reduce_min_sync(0xFFFFFFFFu, best);
+    if (lane == 0) warp_min[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 1; w < kClockThreads / 32; w++) best = min(best, warp_min[w]);
+        clock[c] = (int32_t)(best & 4095u) - e;
     }
 }
 
@@ -724,6 +822,75 @@ __device__ __forceinline__ void demod_produce(const DemodParams &p, int ntile, u
     }
 }
 
+// Producer of the padded layout (k_demod_shift<.., kPad = true>: thread segments of 2^k vectors, 1500 / 750 / 375 baud).
+// A thread per window would read 16-byte vectors 64 / 128 / 256 bytes apart: 4- to 8-way bank conflicts however the
+// windows are dealt.  Here the tile is laid out with ONE spare vector after every thread segment of kV vectors (stride
+// kV + 1: odd, conflict-free), which a bulk copy cannot do: the producer warp issues 16-byte cp.async copies (LDGSTS,
+// 512 consecutive bytes per instruction) with the destination vector v + (v - v0) / kV, v0 = vector of the tile's first
+// sample.  Each lane reports its copies to the stage's full barrier (cp.async.mbarrier.arrive.noinc), the lane that
+// wrote the tile's metadata adds a plain arrival: 33 arrivals per use.
+template <int kV>
+__device__ __forceinline__ void demod_produce_pad(const DemodParams &p, int ntile, uint8_t *stage_base, TileMeta *meta,
+                                                  uint64_t *full, uint64_t *empty, int pw, int npw)
+{
+    static_assert((kV & (kV - 1)) == 0, "vectors per thread segment: a power of two");
+    constexpr int kLog = kV == 4 ? 2 : (kV == 8 ? 3 : (kV == 16 ? 4 : 5));
+    static_assert((1 << kLog) == kV, "kV in 4..32");
+    const int S = p.stages, lane = threadIdx.x & 31;
+    const int G = (int)gridDim.x, first_tile = (int)blockIdx.x;
+    const long long base_mis = (long long)((reinterpret_cast<uintptr_t>(p.samples) >> 1) & 63);
+    int s = 0;
+    uint32_t ph = 0;
+    const uint64_t pol = l2_policy_evict_first();
+    const bool hint = p.l2_hint != 0;
+    const int vstep = 32 * npw, stage_bytes = p.stage_bytes;
+    const uint32_t sdst = afsk_smem_u32(stage_base);
+    const int16_t *samples = p.samples;
+    TileJob next = {};
+    if (lane < ntile) next = demod_tile_job(p, first_tile + lane * G, base_mis);
+    for (int base = 0; base < ntile; base += 32) {
+        const TileJob cur = next;
+        if (base + 32 + lane < ntile) next = demod_tile_job(p, first_tile + (base + 32 + lane) * G, base_mis);
+        const int cnt = min(32, ntile - base);
+        for (int j = 0; j < cnt; j++) {
+            const long long ga = __shfl_sync(0xFFFFFFFFu, cur.ga, j);
+            const int nvec = (int)(__shfl_sync(0xFFFFFFFFu, cur.bytes, j) >> 4);
+            const int v0 = __shfl_sync(0xFFFFFFFFu, cur.m.e0, j) >> 3;
+            if (base + j >= S) {
+                if (lane == 0)
+                    while (!mbar_try_wait(&empty[s], ph ^ 1u)) __nanosleep(64);
+                __syncwarp();
+            }
+            if (lane == j && pw == 0) {
+                meta[s] = cur.m;
+                mbar_arrive(&full[s]);
+            }
+            // vector v0 + u of the copy goes to vector v0 + u + u / kV of the stage; this lane: u = 32 pw + lane + k vstep
+            const int nu = nvec - v0;
+            int u = 32 * pw + lane;
+            uint32_t d = sdst + (uint32_t)s * (uint32_t)stage_bytes + 16u * (uint32_t)(v0 + u);
+            const char *sp = reinterpret_cast<const char *>(samples + ga) + 16 * (v0 + u);
+            if (hint) {
+                for (; u + 3 * vstep < nu; u += 4 * vstep, d += 64u * vstep, sp += 64 * vstep) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        cp_async16_hint(d + 16u * (uint32_t)(k * vstep + ((u + k * vstep) >> kLog)), sp + 16 * k * vstep, pol);
+                }
+                for (; u < nu; u += vstep, d += 16u * vstep, sp += 16 * vstep) cp_async16_hint(d + 16u * (uint32_t)(u >> kLog), sp, pol);
+            } else {
+                for (; u + 3 * vstep < nu; u += 4 * vstep, d += 64u * vstep, sp += 64 * vstep) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        cp_async16(d + 16u * (uint32_t)(k * vstep + ((u + k * vstep) >> kLog)), sp + 16 * k * vstep);
+                }
+                for (; u < nu; u += vstep, d += 16u * vstep, sp += 16 * vstep) cp_async16(d + 16u * (uint32_t)(u >> kLog), sp);
+            }
+            cp_async_mbar_arrive_noinc(&full[s]);
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+    }
+}
+
 // kNT > 0: the number of vector steps per thread is a compile-time constant (fully unrolled, one
 // packed accumulator); kNT == 0: run-time count with a flush every kFlushVecs vectors.
 // kMerge: the thread segment is a multiple of 8 samples, so the partial head vector (slots >= e)
@@ -1059,7 +1226,7 @@ __host__ __device__ constexpr uint32_t tone_weights4(int bf, int pos, bool space
     return w;
 }
 
-template <int kBf, int kWpt, int kE>
+template <int kBf, int kWpt, int kE, bool kPad>
 __device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int thr_bf, int nvalid, uint32_t &bits,
                                              uint32_t &quiet)
 {
@@ -1068,7 +1235,7 @@ __device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int
 #pragma unroll
     for (int i = 0; i <= kV; i++) {
         if (i < kV || kE > 0) {                      // an aligned tile never touches the extra vector
-            const uint4 v = dp[i];
+            const uint4 v = dp[(kPad && i == kV) ? kV + 1 : i];   // padded layout: the next segment starts one vector on
             W[4 * i] = v.x; W[4 * i + 1] = v.y; W[4 * i + 2] = v.z; W[4 * i + 3] = v.w;
         }
     }
@@ -1111,7 +1278,7 @@ __device__ __forceinline__ void shift_decode(const uint4 *dp, uint32_t k512, int
     }
 }
 
-template <int kBf, int kWpt>
+template <int kBf, int kWpt, bool kPad = false>
 __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodParams p)
 {
     static_assert(kBf % 4 == 0 && (kBf * kWpt) % 8 == 0 && 32 % kWpt == 0, "segment must be whole vectors");
@@ -1123,10 +1290,11 @@ __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodPa
     uint64_t *full = reinterpret_cast<uint64_t *>(meta + kMaxStages);
     uint64_t *empty = full + kMaxStages;
     constexpr int kSeg = kBf * kWpt, kLanesPerWord = 32 / kWpt;
+    constexpr int kStride = kSeg / 8 + (kPad ? 1 : 0);       // vectors between the segments of consecutive threads
 
     if (tid == 0) {
         for (int s = 0; s < S; s++) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], kPad ? 32 * p.pad_warps + 1 : 1);
             mbar_init(&empty[s], kConsumerThreads / 32);
         }
         mbar_fence_init();
@@ -1137,6 +1305,14 @@ __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodPa
 
     const int ntile = (p.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + G, ...
     if (ntile <= 0) return;
+    if constexpr (kPad) {
+        // the producer warp and the (otherwise idle) auxiliary warps share the copies of every tile
+        if (warp >= kConsumerThreads / 32) {
+            const int pw = warp - kConsumerThreads / 32;
+            if (pw < p.pad_warps) demod_produce_pad<kSeg / 8>(p, ntile, stage_base, meta, full, empty, pw, p.pad_warps);
+            return;
+        }
+    }
     if (warp == kConsumerThreads / 32) {
         demod_produce(p, ntile, stage_base, meta, full, empty);
         return;
@@ -1160,17 +1336,17 @@ __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodPa
         uint32_t bits = 0, quiet = 0;
         if (m.nwin > wbase) {
             const uint4 *dp = reinterpret_cast<const uint4 *>(stage_base + (size_t)s * p.stage_bytes) + (m.e0 >> 3) +
-                              (u * kConsumerThreads + tid) * (kSeg / 8);
+                              (u * kConsumerThreads + tid) * kStride;
             const int nvalid = m.nwin - wbase - tid * kWpt;
             switch (m.e0 & 7) {                      // uniform over the CTA
-            case 0: shift_decode<kBf, kWpt, 0>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
-            case 1: shift_decode<kBf, kWpt, 1>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
-            case 2: shift_decode<kBf, kWpt, 2>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
-            case 3: shift_decode<kBf, kWpt, 3>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
-            case 4: shift_decode<kBf, kWpt, 4>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
-            case 5: shift_decode<kBf, kWpt, 5>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
-            case 6: shift_decode<kBf, kWpt, 6>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
-            default: shift_decode<kBf, kWpt, 7>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 0: shift_decode<kBf, kWpt, 0, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 1: shift_decode<kBf, kWpt, 1, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 2: shift_decode<kBf, kWpt, 2, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 3: shift_decode<kBf, kWpt, 3, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 4: shift_decode<kBf, kWpt, 4, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 5: shift_decode<kBf, kWpt, 5, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            case 6: shift_decode<kBf, kWpt, 6, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
+            default: shift_decode<kBf, kWpt, 7, kPad>(dp, k512, m.thr_bf, nvalid, bits, quiet); break;
             }
         }
         if (u == p.nsub - 1) {
@@ -1179,12 +1355,18 @@ __global__ void __launch_bounds__(kFusedThreads4, 2) k_demod_shift(const DemodPa
         }
         if (m.nwin > wbase) {
             // kLanesPerWord threads hold the kWpt-bit pieces of one plane word
-            uint32_t bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
-            uint32_t qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
+            uint32_t bw, qw;
+            if (kWpt == 1) {                         // one window per lane: the plane words are warp ballots
+                bw = __ballot_sync(0xFFFFFFFFu, bits != 0u);
+                qw = __ballot_sync(0xFFFFFFFFu, quiet != 0u);
+            } else {
+                bw = bits << (kWpt * (lane & (kLanesPerWord - 1)));
+                qw = quiet << (kWpt * (lane & (kLanesPerWord - 1)));
 #pragma unroll
-            for (int o = 1; o < kLanesPerWord; o <<= 1) {
-                bw |= __shfl_xor_sync(0xFFFFFFFFu, bw, o);
-                qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
+                for (int o = 1; o < kLanesPerWord; o <<= 1) {
+                    bw |= __shfl_xor_sync(0xFFFFFFFFu, bw, o);
+                    qw |= __shfl_xor_sync(0xFFFFFFFFu, qw, o);
+                }
             }
             const int word = (tid * kWpt) >> 5;
             if ((lane & (kLanesPerWord - 1)) == 0 && word * 32 < m.nwin - wbase)
@@ -1945,6 +2127,7 @@ struct Group {
     int bf = 0, tpw_log2 = 0, seg = 0, nv = 0, nt = 0, merge = 0, wt = 0, nsub = 1, stage_bytes = 0, stages = 0;
     int small_wpt = 0;            // > 0: k_demod_lane<bf/8, small_wpt>
     int shift_wpt = 0;            // > 0: k_demod_shift<bf, shift_wpt>
+    int pad = 0;                  // 1: padded layout, k_demod_shift<bf, shift_wpt, true> (cp.async producer)
     size_t smem = 0;
     int grid = 0;
     // fused mode (auxiliary warps): shared memory with the AuxSmem block appended, its offset, the grid for
@@ -1968,6 +2151,8 @@ struct Group {
 
 // k_demod_shift instantiations: (bit length, windows per thread)
 #define AFSK_SHIFT_VARIANTS(X) X(4, 8) X(12, 4) X(20, 2) X(60, 2) X(100, 2) X(120, 1) X(200, 1)
+// the same with the padded layout (thread segments of 8 / 8 / 16 vectors)
+#define AFSK_PAD_VARIANTS(X) X(32, 2) X(64, 1) X(128, 1)
 
 static cudaError_t demod_set_smem_attr()
 {
@@ -1975,6 +2160,10 @@ static cudaError_t demod_set_smem_attr()
 #define X(BF, W) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<BF, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     AFSK_SHIFT_VARIANTS(X)
+#undef X
+#define X(BF, W) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_shift<BF, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    AFSK_PAD_VARIANTS(X)
 #undef X
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<2, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demod_lane<3, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -2003,7 +2192,11 @@ static const void *demod_kernel_of(const Group &g)
     if (g.small_wpt && g.bf == 16) return (const void *)k_demod_lane<2, 4, 8>;
     if (g.small_wpt && g.bf == 24) return (const void *)k_demod_lane<3, 2, 8>;
 #define X(BF, W) \
-    if (g.shift_wpt == (W) && g.bf == (BF)) return (const void *)k_demod_shift<BF, W>;
+    if (g.pad && g.shift_wpt == (W) && g.bf == (BF)) return (const void *)k_demod_shift<BF, W, true>;
+    AFSK_PAD_VARIANTS(X)
+#undef X
+#define X(BF, W) \
+    if (!g.pad && g.shift_wpt == (W) && g.bf == (BF)) return (const void *)k_demod_shift<BF, W>;
     AFSK_SHIFT_VARIANTS(X)
 #undef X
 #define X(NT, MG) \
@@ -2038,7 +2231,7 @@ struct AfskRxPlan {
     int64_t sum_samples = 0;      // over the captures decoded on the GPU
     bool can_fuse = false;        // every group fits the auxiliary warps (bit length, shared memory)
     int fused = -1;               // AFSK_OPT_FUSED: -1 automatic, 0 three kernels, 1 fused clocks, 2 fused clocks and framing
-    int clock_kernel = 1;         // AFSK_OPT_CLOCK_KERNEL: 1 k_clock, 2 k_clock2 (bit lengths up to kAuxMaxBf)
+    int clock_kernel = 0;         // AFSK_OPT_CLOCK_KERNEL: 0 automatic (k_clock_q for bit lengths 8..24, k_clock for the rest), 1 k_clock, 2 k_clock2 (bit lengths up to kAuxMaxBf)
     bool can_clock2 = false;
     int frame_kernel = 0;         // AFSK_OPT_FRAME_KERNEL: 0 automatic, 1 k_frame_warp, 2 k_frame<128,4,int>, 3 <512,8,int>, 4 <512,8,long long>
     int l2_hint = -1;             // AFSK_OPT_L2_HINT / AFSK_L2_HINT (read once per plan): -1 per-kernel default
@@ -2049,6 +2242,7 @@ struct AfskRxPlan {
     // next group's CTAs fill the SMs as the previous group's drain instead of waiting for its last CTA
     int rot = 1;                  // rotated vector order at 32-sample segments (tuning switch AFSK_NO_ROT)
     int group_streams = 1;        // AFSK_OPT_GROUP_STREAMS
+    int pad_warps = 0;            // padded layout: producer warps per CTA, 0 = per group (tuning switch AFSK_PAD_WARPS, read at plan creation)
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> gevents;   // [0] fork, [i] join of group i
 };
@@ -2118,6 +2312,24 @@ static bool configure_group(Group &g, int bf)
         if (long_shift) g.stages = (int)std::min<size_t>(3, (size_t)(220 * 1024) / (size_t)g.stage_bytes);
         g.smem = demod_smem_bytes(g);
         return true;
+    }
+    if ((bf == 32 || bf == 64 || bf == 128) && !getenv("AFSK_NO_PAD")) {
+        // 1500 / 750 / 375 baud: power-of-two windows.  A thread per window (two at 1500 baud) over the padded layout
+        // (demod_produce_pad): 8 / 8 / 16 vectors per thread segment and one spare vector after each.  Tiles of 37 KB in
+        // a 3-stage ring with two CTAs per SM (70 KB tiles, one CTA per SM at 375 baud, like the long k_demod_shift windows).
+        g.shift_wpt = bf == 32 ? 2 : 1;
+        g.pad = 1;
+        g.seg = bf * g.shift_wpt;
+        g.nv = g.seg / 8 + 1;
+        g.nt = g.nv; g.merge = 0;
+        g.nsub = 1;
+        if (const char *ev = getenv("AFSK_DEMOD_NSUB")) g.nsub = std::max(1, std::min(8, atoi(ev)));
+        g.wt = g.nsub * kConsumerThreads * g.shift_wpt;
+        g.stage_bytes = (((8 + g.nsub * kConsumerThreads * (g.seg / 8 + 1) + 2) * 16) + 127) & ~127;
+        g.stages = (int)std::min<size_t>(3, (size_t)(220 * 1024) / (size_t)g.stage_bytes);
+        if (const char *ev = getenv("AFSK_DEMOD_STAGES")) g.stages = std::max(1, std::min(kMaxStages, atoi(ev)));
+        g.smem = demod_smem_bytes(g);
+        return g.smem <= 227 * 1024;
     }
     // Segments of at most 48 samples per thread.  The thread stride in shared memory is 2 * seg bytes:
     // 40 samples (80 B) is conflict-free for 128-bit loads and 48 is 2-way, both reach the HBM ceiling;
@@ -2408,8 +2620,10 @@ int afsk_rx_plan_create_ranges(int device, int B, const int64_t *h_start, const 
     if (getenv("AFSK_NO_ROT")) P->rot = 0;
     ev = getenv("AFSK_GROUP_STREAMS");
     if (ev) P->group_streams = atoi(ev) ? 1 : 0;
+    ev = getenv("AFSK_PAD_WARPS");
+    if (ev) P->pad_warps = std::max(1, std::min(5, atoi(ev)));
     ev = getenv("AFSK_CLOCK_KERNEL");
-    if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) P->clock_kernel = atoi(ev);
+    if (ev && atoi(ev) >= 0 && atoi(ev) <= 2) P->clock_kernel = atoi(ev);
     ev = getenv("AFSK_FRAME_KERNEL");
     if (ev && atoi(ev) >= 0 && atoi(ev) <= 4) P->frame_kernel = atoi(ev);
     const int rc = plan_build(P, B, h_start, h_len, h_baud, h_amp_end);
@@ -2468,7 +2682,7 @@ int afsk_rx_plan_set_option(AfskRxPlan *P, int option, int value)
         P->group_streams = value ? 1 : 0;
         return AFSK_OK;
     case AFSK_OPT_CLOCK_KERNEL:
-        if (value != 1 && value != 2) { afsk_set_error("AFSK_OPT_CLOCK_KERNEL: 1 or 2"); return AFSK_E_ARG; }
+        if (value < 0 || value > 2) { afsk_set_error("AFSK_OPT_CLOCK_KERNEL: 0, 1 or 2"); return AFSK_E_ARG; }
         P->clock_kernel = value;
         return AFSK_OK;
     case AFSK_OPT_FUSED:
@@ -2510,12 +2724,24 @@ static int plan_fused_level(const AfskRxPlan *P)
 static bool plan_fused(const AfskRxPlan *P) { return plan_fused_level(P) >= 1; }
 static bool plan_fused_frame(const AfskRxPlan *P) { return plan_fused_level(P) >= 2; }
 
+// clock recovery launches of the three-kernel schedule (same selection as afsk_rx_decode)
+static bool clock_q_group(const Group &g) { return !g.caps.empty() && g.bf % 4 == 0 && g.bf >= 8 && g.bf <= 24; }
+static int plan_clock_launches(const AfskRxPlan *P)
+{
+    if (P->clock_kernel != 0) return 1;
+    int n = 0;
+    int64_t qcaps = 0;
+    for (const Group &g : P->groups)
+        if (clock_q_group(g)) { n++; qcaps += (int64_t)g.caps.size(); }
+    return n + (qcaps < P->B ? 1 : 0);
+}
+
 int afsk_rx_plan_launches(const AfskRxPlan *P, int *launches)
 {
     if (!P || !launches) return AFSK_E_ARG;
     if (P->B == 0) *launches = 0;
     else if (plan_fused(P)) *launches = (int)P->groups.size() + (P->n_preset > 0 ? 1 : 0) + (plan_fused_frame(P) ? 0 : 1);
-    else *launches = 2 + (int)P->groups.size();
+    else *launches = plan_clock_launches(P) + 1 + (int)P->groups.size();
     return AFSK_OK;
 }
 
@@ -2574,7 +2800,26 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
     } else if (P->clock_kernel == 2 && P->can_clock2) {
         k_clock2<<<P->B, 128, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
     } else {
-        k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res);
+        // automatic: the short-bit groups through k_clock_q (registers only), everything else through k_clock, which
+        // leaves the captures of those groups alone (and is not launched at all when they are the whole batch)
+        uint32_t qmask = 0;
+        int64_t qcaps = 0;
+        if (P->clock_kernel == 0) {
+            for (const Group &g : P->groups) {
+                if (!clock_q_group(g)) continue;
+                const int ng = (int)g.caps.size();
+                switch (g.bf) {
+                case 8: k_clock_q<2><<<ng, kClockThreads, 0, st>>>(d_samples, P->d_caps, g.d_caps, P->d_clock); break;
+                case 12: k_clock_q<3><<<ng, kClockThreads, 0, st>>>(d_samples, P->d_caps, g.d_caps, P->d_clock); break;
+                case 16: k_clock_q<4><<<ng, kClockThreads, 0, st>>>(d_samples, P->d_caps, g.d_caps, P->d_clock); break;
+                case 20: k_clock_q<5><<<ng, kClockThreads, 0, st>>>(d_samples, P->d_caps, g.d_caps, P->d_clock); break;
+                default: k_clock_q<6><<<ng, kClockThreads, 0, st>>>(d_samples, P->d_caps, g.d_caps, P->d_clock); break;
+                }
+                qmask |= 1u << (g.bf >> 2);
+                qcaps += ng;
+            }
+        }
+        if (qcaps < P->B) k_clock<<<P->B, kClockThreads, 0, st>>>(d_samples, P->d_caps, P->d_clock, d_res, qmask);
     }
     const int ngroups = (int)P->groups.size();
     const bool multi = P->group_streams != 0 && ngroups > 1;
@@ -2613,12 +2858,13 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 (environment, read at
         // plan creation) or AFSK_OPT_L2_HINT force it.
         p.l2_hint = P->l2_hint >= 0 ? P->l2_hint : (g.small_wpt ? 0 : 1);
+        p.pad_warps = P->pad_warps > 0 ? P->pad_warps : (g.bf == 128 ? 3 : 2);   // same box: 750 baud 5572 / 5906 / 5714 / 5750 GB/s with 1 / 2 / 3 / 5 warps, 375 baud (one CTA per SM) 3782 / 6194 / 6328 / 6054
         p.fused = fused ? 1 : 0; p.fused_frame = fused_frame ? 1 : 0;
         p.epoch = P->epoch; p.aux_off = g.aux_off; p.clk_magic = g.clk_magic; p.clk_shift = g.clk_shift;
         p.cready = P->d_cready; p.clock_out = P->d_clock; p.tiles_done = g.d_tiles_done; p.ctrl = g.d_ctrl;
         p.out = d_out; p.res = d_res;
         const int grid = fused ? g.grid_fused : g.grid;
-        const int block = !fused ? kDemodThreads : ((g.small_wpt || g.shift_wpt) ? kFusedThreads4 : kFusedThreads2);
+        const int block = g.pad ? kFusedThreads4 : (!fused ? kDemodThreads : ((g.small_wpt || g.shift_wpt) ? kFusedThreads4 : kFusedThreads2));
         const size_t smem = fused ? g.smem_fused : g.smem;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (!multi && P->timing && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
@@ -2627,7 +2873,11 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         else if (g.small_wpt && g.bf == 16) k_demod_lane<2, 4, 8><<<grid, block, smem, gs>>>(p);
         else if (g.small_wpt && g.bf == 24) k_demod_lane<3, 2, 8><<<grid, block, smem, gs>>>(p);
 #define X(BF, W) \
-        else if (g.shift_wpt == (W) && g.bf == (BF)) k_demod_shift<BF, W><<<grid, block, smem, gs>>>(p);
+        else if (g.pad && g.shift_wpt == (W) && g.bf == (BF)) k_demod_shift<BF, W, true><<<grid, block, smem, gs>>>(p);
+        AFSK_PAD_VARIANTS(X)
+#undef X
+#define X(BF, W) \
+        else if (!g.pad && g.shift_wpt == (W) && g.bf == (BF)) k_demod_shift<BF, W><<<grid, block, smem, gs>>>(p);
         AFSK_SHIFT_VARIANTS(X)
 #undef X
         else launch_demod(g.merge, g.nt, grid, block, smem, gs, p);

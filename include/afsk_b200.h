@@ -123,9 +123,11 @@ int afsk_rx_plan_destroy(AfskRxPlan *plan);
                                    profiles/r2_tuning_log.md; both stay available and parity-tested).  Bit lengths over
                                    185 frames (below 260 baud) keep the three kernels; captures of more than 2^18 bit
                                    windows keep the separate framing kernel. */
-#define AFSK_OPT_CLOCK_KERNEL 4 /* clock recovery kernel of the three-kernel schedule: 1 k_clock (two sweeps over candidate
-                                   distances kept in registers), 2 k_clock2 (one sweep with an exact multiply-shift floor,
-                                   half the shared memory; bit lengths up to 185 frames, else k_clock) */
+#define AFSK_OPT_CLOCK_KERNEL 4 /* clock recovery kernel of the three-kernel schedule: 0 (default) automatic = k_clock_q
+                                   (32 candidates per thread from registers, no prefix array) for bit lengths of 8..24
+                                   frames (6000..2000 baud) and k_clock for the rest; 1 k_clock everywhere (two sweeps
+                                   over candidate distances kept in registers); 2 k_clock2 (one sweep with an exact
+                                   multiply-shift floor, half the shared memory; bit lengths up to 185 frames, else k_clock) */
 #define AFSK_OPT_GROUP_STREAMS 5 /* 1 (default): the demodulator launches of a mixed-baud batch (one per bit length) run on
                                    streams of their own between the clock and framing kernels, so that one group's CTAs
                                    fill the SMs as the previous group's drain; 0: one after the other on the caller's stream */

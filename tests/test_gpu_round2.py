@@ -291,8 +291,20 @@ def _decode_with(samples, offsets, baud, thr, fused, frame_kernel=0, repeats=1):
     return out, n.value
 
 
+def test_fused_request_with_a_padded_layout_group_keeps_three_kernels():
+    """1500 / 750 / 375 baud use the padded layout, whose ring leaves no shared memory for the auxiliary warps at two
+    CTAs per SM: a batch holding such a group is decoded by the three kernels whatever AFSK_OPT_FUSED says."""
+    caps, baud, thr, _ = _mixed_corpus(53, 60, bauds=(1200, 6000, 1500, 750, 375))
+    samples, offsets = A.modem._concat(caps)
+    three, n3 = _decode_with(samples, offsets, baud, thr, 0)
+    fused, nf = _decode_with(samples, offsets, baud, thr, 2)
+    assert nf == n3
+    assert np.array_equal(three.results, fused.results) and three.payloads() == fused.payloads()
+    _assert_equals_oracle(fused, caps, baud, thr)
+
+
 def test_fused_equals_three_kernels_and_oracle_mixed():
-    caps, baud, thr, _ = _mixed_corpus(51, 160, bauds=(300, 600, 1200, 2400, 4000, 6000, 4800, 9600, 1500, 800, 2000, 3000, 375))
+    caps, baud, thr, _ = _mixed_corpus(51, 160, bauds=(300, 600, 1200, 2400, 4000, 6000, 4800, 9600, 800, 2000, 3000, 480))
     samples, offsets = A.modem._concat(caps)
     three, n3 = _decode_with(samples, offsets, baud, thr, 0)
     fused, nf = _decode_with(samples, offsets, baud, thr, 2, repeats=4)
@@ -381,9 +393,11 @@ def test_fused_long_capture_and_retargeted_plan():
         rx.close()
 
 
-@pytest.mark.parametrize("baud", [6000, 1200, 300, 2400, 4000, 1500, 800])
-def test_clock_kernel_variant_2(baud):
-    """k_clock2 (AFSK_OPT_CLOCK_KERNEL = 2): the one-sweep clock search as a kernel of its own == k_clock == oracle."""
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("baud", [6000, 1200, 300, 2400, 4000, 1500, 800, 3000, 2000])
+def test_clock_kernel_variant_2(baud, variant):
+    """k_clock for every bit length (AFSK_OPT_CLOCK_KERNEL = 1; the default sends 6000..2000 baud through k_clock_q) and
+    k_clock2 (= 2): the one-sweep clock search as a kernel of its own == oracle."""
     rng = np.random.default_rng([61, baud])
     bf = 48000 // baud
     caps = []
@@ -398,7 +412,47 @@ def test_clock_kernel_variant_2(baud):
     thr = np.full(len(caps), 14000, np.int32)
     samples, offsets = A.modem._concat(caps)
     s = A.RxSession(offsets, b, thr)
-    _cabi.check(_cabi.lib().afsk_rx_plan_set_option(s.plan, _cabi.OPT_CLOCK_KERNEL, 2))
+    _cabi.check(_cabi.lib().afsk_rx_plan_set_option(s.plan, _cabi.OPT_CLOCK_KERNEL, variant))
     s.upload(samples); s.run()
     _assert_equals_oracle(s.download(), caps, b, thr)
+    s.close()
+
+
+@pytest.mark.parametrize("baud", [6000, 4000, 3000, 2400, 2000])
+def test_clock_q_every_start_alignment(baud):
+    """k_clock_q (the default at 6000..2000 baud): every capture start modulo 8 samples, lead-ins that put the first minimum
+    near both ends of the candidate range, noise-only and constant captures; mixed with a 1200-baud capture and a short
+    one so that k_clock runs beside it on the rest of the batch."""
+    rng = np.random.default_rng([67, baud])
+    bf = 48000 // baud
+    caps, bd = [], []
+    for i in range(64):
+        fr = O.tx_frames(rng.integers(0, 256, 12, dtype=np.uint8).tobytes(), baud, 0.1)
+        lead = int(rng.choice([0, 1, bf - 1, 2 * bf + 7, 4096 - 2 * bf - 1, 4096 - 2 * bf, 4090])) if i % 4 == 0 else int(rng.integers(0, 64))
+        x = np.concatenate([np.zeros(lead, np.int16), fr]).astype(np.int32)
+        if i % 3 == 1:
+            x = x + np.round(rng.normal(0, float(rng.choice([4000, 15000, 30000])), len(x))).astype(np.int32)
+        if i % 16 == 5:
+            x = np.round(rng.normal(0, 12000, len(x))).astype(np.int32)
+        if i == 40:
+            x = np.full(4500, -32768, np.int32)
+        if i == 41:
+            x = np.full(4500, 32767, np.int32)
+        x = np.clip(x, -32768, 32767).astype(np.int16)
+        caps.append(x[:len(x) - int(rng.integers(0, 8))])        # lengths of every residue: the next start moves
+        bd.append(baud)
+    caps.insert(7, O.tx_frames(b"beside", 1200, 0.1)); bd.insert(7, 1200)
+    caps.insert(9, np.zeros(3000, np.int16)); bd.insert(9, baud)
+    b = np.array(bd, np.int32)
+    thr = np.full(len(caps), 14000, np.int32)
+    samples, offsets = A.modem._concat(caps)
+    assert len({int(o) % 8 for o in offsets[:-1]}) == 8
+    s = A.RxSession(offsets, b, thr)
+    s.upload(samples); s.run()
+    got = s.download()
+    _assert_equals_oracle(got, caps, b, thr)
+    _cabi.check(_cabi.lib().afsk_rx_plan_set_option(s.plan, _cabi.OPT_CLOCK_KERNEL, 1))
+    s.run()
+    ref = s.download()
+    assert np.array_equal(got.results, ref.results) and got.payloads() == ref.payloads()
     s.close()

@@ -21,8 +21,10 @@ import bench  # noqa: E402
 def main():
     wl = sys.argv[1]
     variants = sys.argv[2:] or [""]
-    B = bench.set_workload(wl, 0)
-    samples, offsets, spec = bench.build_batch_on_gpu(B, 0, 0)
+    B = bench.resolve_workload(wl)[2]
+    corpus = bench.Corpus(wl, B)
+    samples, offsets = bench.build_on_gpu(corpus, 0, B, 0)
+    spec = corpus.spec(0, B)
     total = int(offsets[-1])
     stream = torch.cuda.current_stream().cuda_stream
     knobs = sorted({kv.split("=")[0] for v in variants for kv in v.split(",") if kv})
@@ -39,7 +41,7 @@ def main():
     for v in variants:
         setenv(v)
         s = A.RxSession(offsets, spec["baud_rx"], spec["amp_end"], 0)
-        s.bind(samples.data_ptr())
+        s.bind(samples.data_ptr(), samples.numel())
         sessions.append(s)
     times = [[] for _ in variants]
     steps = [[] for _ in variants]

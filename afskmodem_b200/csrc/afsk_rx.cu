@@ -133,6 +133,16 @@ __device__ __forceinline__ long long num_windows(long long n, int bf, int clk)
     return span > 0 ? (span + bf - 1) / bf : 0;
 }
 
+// Waiting on another CTA of the same launch (fused schedule): a wait that has lasted four seconds is a scheduling
+// bug, and an aborted launch (cudaErrorLaunchFailure at the next synchronisation) is better than a hung device.
+__device__ __forceinline__ void spin_guard(unsigned long long &t0)
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000ull) __trap();
+}
+
 // ------------------------------------------------------------------------------ k_clock ----
 __global__ void __launch_bounds__(kClockThreads) k_clock(const int16_t *__restrict__ x,
                                                          const CapDesc *__restrict__ caps,
@@ -749,7 +759,8 @@ __device__ __forceinline__ TileJob demod_tile_job(const DemodParams &p, int it, 
     if (p.fused) {
         // the capture's clock job was handed out before any job of a later capture and never blocks
         unsigned long long w = ld_relaxed_u64(p.cready + c);
-        while ((uint32_t)(w >> 32) != p.epoch) { __nanosleep(200); w = ld_relaxed_u64(p.cready + c); }
+        unsigned long long t0 = 0;
+        while ((uint32_t)(w >> 32) != p.epoch) { __nanosleep(200); spin_guard(t0); w = ld_relaxed_u64(p.cready + c); }
         clk = (int)(uint32_t)w;
     } else {
         clk = p.clock[c];
@@ -833,9 +844,6 @@ template <int kV>
 __device__ __forceinline__ void demod_produce_pad(const DemodParams &p, int ntile, uint8_t *stage_base, TileMeta *meta,
                                                   uint64_t *full, uint64_t *empty, int pw, int npw)
 {
-    static_assert((kV & (kV - 1)) == 0, "vectors per thread segment: a power of two");
-    constexpr int kLog = kV == 4 ? 2 : (kV == 8 ? 3 : (kV == 16 ? 4 : 5));
-    static_assert((1 << kLog) == kV, "kV in 4..32");
     const int S = p.stages, lane = threadIdx.x & 31;
     const int G = (int)gridDim.x, first_tile = (int)blockIdx.x;
     const long long base_mis = (long long)((reinterpret_cast<uintptr_t>(p.samples) >> 1) & 63);
@@ -874,16 +882,16 @@ __device__ __forceinline__ void demod_produce_pad(const DemodParams &p, int ntil
                 for (; u + 3 * vstep < nu; u += 4 * vstep, d += 64u * vstep, sp += 64 * vstep) {
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        cp_async16_hint(d + 16u * (uint32_t)(k * vstep + ((u + k * vstep) >> kLog)), sp + 16 * k * vstep, pol);
+                        cp_async16_hint(d + 16u * (uint32_t)(k * vstep) + 16u * ((uint32_t)(u + k * vstep) / (uint32_t)kV), sp + 16 * k * vstep, pol);
                 }
-                for (; u < nu; u += vstep, d += 16u * vstep, sp += 16 * vstep) cp_async16_hint(d + 16u * (uint32_t)(u >> kLog), sp, pol);
+                for (; u < nu; u += vstep, d += 16u * vstep, sp += 16 * vstep) cp_async16_hint(d + 16u * ((uint32_t)u / (uint32_t)kV), sp, pol);
             } else {
                 for (; u + 3 * vstep < nu; u += 4 * vstep, d += 64u * vstep, sp += 64 * vstep) {
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        cp_async16(d + 16u * (uint32_t)(k * vstep + ((u + k * vstep) >> kLog)), sp + 16 * k * vstep);
+                        cp_async16(d + 16u * (uint32_t)(k * vstep) + 16u * ((uint32_t)(u + k * vstep) / (uint32_t)kV), sp + 16 * k * vstep);
                 }
-                for (; u < nu; u += vstep, d += 16u * vstep, sp += 16 * vstep) cp_async16(d + 16u * (uint32_t)(u >> kLog), sp);
+                for (; u < nu; u += vstep, d += 16u * vstep, sp += 16 * vstep) cp_async16(d + 16u * ((uint32_t)u / (uint32_t)kV), sp);
             }
             cp_async_mbar_arrive_noinc(&full[s]);
             if (++s == S) { s = 0; ph ^= 1u; }
@@ -1803,16 +1811,14 @@ __device__ __forceinline__ void frame_capture_warp(int c, const CapDesc &d, int 
         for (int u = 0; u < kQ; u++) {
             const int i = i0 + 32 * u;
             if (i < nquad) {
+                // the quad's 56 coded bits as a stream (v: bits 0..31, v1: bits 32..63), eight 7-bit codewords cut out of it
                 const uint32_t sh = (uint32_t)((k0 + 56 * i) & 31);
-                uint32_t word = 0;
-#pragma unroll
-                for (int jb = 0; jb < 4; jb++) {
-                    const uint32_t sft = sh + 14u * jb;                 // 0 .. 73
-                    const uint32_t a = sft < 32 ? w[u][0] : (sft < 64 ? w[u][1] : w[u][2]);
-                    const uint32_t bb = sft < 32 ? w[u][1] : (sft < 64 ? w[u][2] : 0u);
-                    word |= decode_byte(__funnelshift_r(a, bb, sft & 31u) & 0x3FFFu, lut) << (8 * jb);
-                }
-                reinterpret_cast<uint32_t *>(o)[i] = word;
+                const uint32_t v = __funnelshift_r(w[u][0], w[u][1], sh), v1 = __funnelshift_r(w[u][1], w[u][2], sh);
+                const uint32_t n0 = lut[v & 0x7Fu], n1 = lut[(v >> 7) & 0x7Fu], n2 = lut[(v >> 14) & 0x7Fu], n3 = lut[(v >> 21) & 0x7Fu];
+                const uint32_t n4 = lut[__funnelshift_r(v, v1, 28) & 0x7Fu], n5 = lut[(v1 >> 3) & 0x7Fu];
+                const uint32_t n6 = lut[(v1 >> 10) & 0x7Fu], n7 = lut[(v1 >> 17) & 0x7Fu];
+                // first nibble of a byte high (:393-399), bytes little-endian in the stored word
+                reinterpret_cast<uint32_t *>(o)[i] = (n0 << 4) | n1 | (n2 << 12) | (n3 << 8) | (n4 << 20) | (n5 << 16) | (n6 << 28) | (n7 << 24);
             }
         }
     }
@@ -1940,9 +1946,11 @@ __device__ __forceinline__ void demod_aux(const DemodParams &p, uint8_t *smem)
     //      tiles have reported: this waits for other CTAs, all of which are resident (the grid is sized to
     //      the device's capacity for this kernel). ----
     uint32_t backoff = 100;
+    unsigned long long t0 = 0;
     while (fnext < p.ng) {
-        if (aux_try_frame(p, S, fnext, lane)) { fnext += fstride; backoff = 100; continue; }
+        if (aux_try_frame(p, S, fnext, lane)) { fnext += fstride; backoff = 100; t0 = 0; continue; }
         __nanosleep(backoff);
+        spin_guard(t0);
         backoff = backoff < 1600 ? backoff * 2 : backoff;
     }
     {
@@ -2317,6 +2325,8 @@ static bool configure_group(Group &g, int bf)
         // 1500 / 750 / 375 baud: power-of-two windows.  A thread per window (two at 1500 baud) over the padded layout
         // (demod_produce_pad): 8 / 8 / 16 vectors per thread segment and one spare vector after each.  Tiles of 37 KB in
         // a 3-stage ring with two CTAs per SM (70 KB tiles, one CTA per SM at 375 baud, like the long k_demod_shift windows).
+        // Same box, general kernel -> padded: 1500 baud 4994 -> 5901 GB/s, 750 baud 4147 -> 5906, 375 baud 4050 -> 6328.
+        // (Measured and rejected: the same layout at 300 / 600 / 4000 baud, 5908 / 5795 / 6364 against 6210 / 6277 / 6357.)
         g.shift_wpt = bf == 32 ? 2 : 1;
         g.pad = 1;
         g.seg = bf * g.shift_wpt;
@@ -2542,7 +2552,8 @@ static int plan_build(AfskRxPlan *P, int B, const int64_t *h_start, const int64_
             g.aux_off = (int)((g.smem + 15) & ~(size_t)15);
             g.smem_fused = (size_t)g.aux_off + sizeof(AuxSmem);
             const int per_sm_f = g.smem_fused <= 113 * 1024 ? 2 : 1;
-            g.can_fuse = g.bf <= kAuxMaxBf && g.smem_fused <= 227 * 1024 && per_sm_f == per_sm;
+            // (the padded-layout kernel's auxiliary warps share the copies of every tile: no fused schedule there)
+            g.can_fuse = g.bf <= kAuxMaxBf && g.smem_fused <= 227 * 1024 && per_sm_f == per_sm && !g.pad;
             g.grid_fused = std::max(1, std::min(total, P->sm_count * per_sm_f));
             // floor(D / d) == (D * magic) >> shift for every D < 2^28, d = 2 bf (Granlund-Montgomery: l = ceil(log2 d),
             // magic = ceil(2^(28 + l) / d) < 2^29)
@@ -2858,7 +2869,7 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 (environment, read at
         // plan creation) or AFSK_OPT_L2_HINT force it.
         p.l2_hint = P->l2_hint >= 0 ? P->l2_hint : (g.small_wpt ? 0 : 1);
-        p.pad_warps = P->pad_warps > 0 ? P->pad_warps : (g.bf == 128 ? 3 : 2);   // same box: 750 baud 5572 / 5906 / 5714 / 5750 GB/s with 1 / 2 / 3 / 5 warps, 375 baud (one CTA per SM) 3782 / 6194 / 6328 / 6054
+        p.pad_warps = P->pad_warps > 0 ? P->pad_warps : (g.smem > 113 * 1024 ? 3 : 2);   // same box: 750 baud 5572 / 5906 / 5714 / 5750 GB/s with 1 / 2 / 3 / 5 warps, 375 baud (one CTA per SM) 3782 / 6194 / 6328 / 6054
         p.fused = fused ? 1 : 0; p.fused_frame = fused_frame ? 1 : 0;
         p.epoch = P->epoch; p.aux_off = g.aux_off; p.clk_magic = g.clk_magic; p.clk_shift = g.clk_shift;
         p.cready = P->d_cready; p.clock_out = P->d_clock; p.tiles_done = g.d_tiles_done; p.ctrl = g.d_ctrl;

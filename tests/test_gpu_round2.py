@@ -159,6 +159,46 @@ def test_every_framing_kernel_variant(kernel):
     s.close()
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_framing_search_step_boundaries(kernel):
+    """The framing kernels search the packed planes in steps of 256 words per warp (8 words per lane): captures of
+    about 20,480 bit windows (640 plane words, two and a half steps) whose data ends inside the last plane words or is
+    cut off by the end of the capture, with the terminator in the first plane word, without a terminator, without a
+    quiet window, and all quiet — against the oracle."""
+    rng = np.random.default_rng(77)
+    caps, baud = [], []
+    for bd, bf in ((6000, 8), (2400, 20), (1200, 40)):
+        for dk in (-33, -32, -31, -2, -1, 0, 1, 2, 31, 32, 33):
+            # payload sized so that the data ends inside the last plane words of a 20,480-window capture
+            tsec = float(rng.choice([0.02, 0.2]))
+            nbytes = (20480 - int(bd * tsec) - 40) // 14 - int(rng.integers(0, 80))   # ends inside the last words, or is cut off
+            fr = O.tx_frames(rng.integers(0, 256, nbytes, dtype=np.uint8).tobytes(), bd, tsec)
+            n = (20480 + dk) * bf + int(rng.integers(0, bf)) + bf
+            x = np.zeros(n, np.int16)
+            lead = int(rng.integers(0, 2 * bf))
+            m = min(len(fr), n - lead)
+            x[lead:lead + m] = fr[:m]
+            caps.append(x); baud.append(bd)
+        # terminator in the first plane word, data to the very end of the capture (no quiet window)
+        fr = O.tx_frames(rng.integers(0, 256, 1400, dtype=np.uint8).tobytes(), bd, 8.0 / bd)
+        caps.append(fr[:20470 * bf].copy()); baud.append(bd)
+        # no terminator at all: training tone only, then loud noise (never quiet), then silence
+        t = O.tx_frames(b"", bd, 1.0)[: 3000 * bf]
+        caps.append(np.concatenate([t, rng.integers(-30000, 30000, 500 * bf).astype(np.int16), np.zeros(40 * bf, np.int16)]))
+        baud.append(bd)
+        caps.append(np.zeros(20480 * bf, np.int16)); baud.append(bd)
+    baud = np.array(baud, np.int32); thr = np.full(len(caps), 14000, np.int32)
+    samples, offsets = A.modem._concat(caps)
+    s = A.RxSession(offsets, baud, thr)
+    _cabi.check(_cabi.lib().afsk_rx_plan_set_option(s.plan, _cabi.OPT_FRAME_KERNEL, kernel))
+    s.upload(samples); s.run()
+    got = s.download()
+    windows = [(len(c) - (bf0 := 48000 // int(b)) - max(int(k), 0) + bf0 - 1) // bf0 for c, b, k in zip(caps, baud, got.clock)]
+    assert min(windows) < 20480 - 30 and max(windows) > 20480 + 30      # both sides of the bound were exercised
+    _assert_equals_oracle(got, caps, baud, thr)
+    s.close()
+
+
 def test_config4_noisy_full_size_capture_vs_oracle():
     """One BASELINE config-4 capture at FULL size (64 KB payload at 300 baud: 146,830,080 frames) with AWGN
     over the whole capture and a lead of silence, decoded by the long-capture path (k_frame<512,8,int>):

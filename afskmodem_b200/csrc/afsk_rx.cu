@@ -129,8 +129,12 @@ struct DemodParams {
 __device__ __forceinline__ long long num_windows(long long n, int bf, int clk)
 {
     // K = #{k >= 0 : clk + k*bf < n - bf}   (afskmodem.py:362,372 — strict)
-    long long span = n - bf - clk;
-    return span > 0 ? (span + bf - 1) / bf : 0;
+    const long long span = n - bf - clk;
+    if (span <= 0) return 0;
+    // captures of fewer than 2^31 samples (all but config-4-sized ones): a 32-bit division instead of the ~100 instructions
+    // of a 64-bit one, which showed in the per-capture framing kernel
+    if (span < (1ll << 31) - 4096) return (long long)(((uint32_t)span + (uint32_t)bf - 1u) / (uint32_t)bf);
+    return (span + bf - 1) / bf;
 }
 
 // Waiting on another CTA of the same launch (fused schedule): a wait that has lasted four seconds is a scheduling
@@ -2159,8 +2163,8 @@ struct Group {
 
 // k_demod_shift instantiations: (bit length, windows per thread)
 #define AFSK_SHIFT_VARIANTS(X) X(4, 8) X(12, 4) X(20, 2) X(60, 2) X(100, 2) X(120, 1) X(200, 1)
-// the same with the padded layout (thread segments of 8 / 8 / 16 vectors)
-#define AFSK_PAD_VARIANTS(X) X(32, 2) X(64, 1) X(128, 1)
+// the same with the padded layout (thread segments of 16 vectors)
+#define AFSK_PAD_VARIANTS(X) X(32, 4) X(64, 2) X(128, 1)
 
 static cudaError_t demod_set_smem_attr()
 {
@@ -2322,12 +2326,14 @@ static bool configure_group(Group &g, int bf)
         return true;
     }
     if ((bf == 32 || bf == 64 || bf == 128) && !getenv("AFSK_NO_PAD")) {
-        // 1500 / 750 / 375 baud: power-of-two windows.  A thread per window (two at 1500 baud) over the padded layout
-        // (demod_produce_pad): 8 / 8 / 16 vectors per thread segment and one spare vector after each.  Tiles of 37 KB in
-        // a 3-stage ring with two CTAs per SM (70 KB tiles, one CTA per SM at 375 baud, like the long k_demod_shift windows).
-        // Same box, general kernel -> padded: 1500 baud 4994 -> 5901 GB/s, 750 baud 4147 -> 5906, 375 baud 4050 -> 6328.
+        // 1500 / 750 / 375 baud: power-of-two windows.  Four / two / one windows per thread over the padded layout
+        // (demod_produce_pad): 16 vectors per thread segment and one spare vector after each (stride 17 vectors: conflict-free
+        // 128-bit reads).  Tiles of 70 KB in a 3-stage ring, one CTA per SM, like the long k_demod_shift windows.
+        // Same box, general kernel -> padded: 1500 baud 4994 -> 5901 GB/s, 750 baud 4147 -> 5906, 375 baud 4050 -> 6328;
+        // segments of 8 -> 16 vectors at 1500 / 750 baud (37 KB tiles, two CTAs per SM before): 5811 -> 6120 and 5717 -> 6232
+        // (the per-window epilogue and the per-thread head / tail handling are shared by twice the samples).
         // (Measured and rejected: the same layout at 300 / 600 / 4000 baud, 5908 / 5795 / 6364 against 6210 / 6277 / 6357.)
-        g.shift_wpt = bf == 32 ? 2 : 1;
+        g.shift_wpt = 128 / bf;
         g.pad = 1;
         g.seg = bf * g.shift_wpt;
         g.nv = g.seg / 8 + 1;
@@ -2869,7 +2875,9 @@ int afsk_rx_decode(AfskRxPlan *P, const int16_t *d_samples, uint8_t *d_out, Afsk
         // depending on the box, so the short-window kernel keeps the default policy.  AFSK_L2_HINT=0/1 (environment, read at
         // plan creation) or AFSK_OPT_L2_HINT force it.
         p.l2_hint = P->l2_hint >= 0 ? P->l2_hint : (g.small_wpt ? 0 : 1);
-        p.pad_warps = P->pad_warps > 0 ? P->pad_warps : (g.smem > 113 * 1024 ? 3 : 2);   // same box: 750 baud 5572 / 5906 / 5714 / 5750 GB/s with 1 / 2 / 3 / 5 warps, 375 baud (one CTA per SM) 3782 / 6194 / 6328 / 6054
+        // producer warps of the padded layout, 16-vector segments (one CTA per SM), two boxes: 750 baud 5267 / 5841-5969 / 6118-6232 /
+        // 5503 GB/s with 2 / 3 / 4 / 5 warps, 1500 baud 5757 / 5758-6120 / 6042-6055 / 5006, 375 baud - / 6026-6328 / 6339 / 5846-6054
+        p.pad_warps = P->pad_warps > 0 ? P->pad_warps : 4;
         p.fused = fused ? 1 : 0; p.fused_frame = fused_frame ? 1 : 0;
         p.epoch = P->epoch; p.aux_off = g.aux_off; p.clk_magic = g.clk_magic; p.clk_shift = g.clk_shift;
         p.cready = P->d_cready; p.clock_out = P->d_clock; p.tiles_done = g.d_tiles_done; p.ctrl = g.d_ctrl;

@@ -14,10 +14,10 @@ import numpy as np
 
 # k_demod* throughput in GB/s of int16 samples by samples-per-bit (48000 / baud), B200, device-resident
 # (tools/baud_sweep.py; profiles/r2_baud_sweep.json).  Bit lengths that are not in the table: DEMOD_GBS_DEFAULT.
-DEMOD_GBS = {200: 3441, 160: 6318, 128: 4867, 120: 4785, 100: 3979, 96: 6726, 80: 6357, 64: 5590, 60: 4951, 48: 7052,
-             40: 6999, 32: 6041, 24: 6814, 20: 6334, 16: 6750, 12: 6142, 8: 6530, 4: 1287}
+DEMOD_GBS = {200: 6960, 160: 6399, 128: 6235, 120: 6924, 100: 7032, 96: 6826, 80: 6370, 64: 6285, 60: 6953, 48: 7092,
+             40: 7029, 32: 5859, 24: 6812, 20: 6384, 16: 6774, 12: 6283, 8: 6551, 4: 2902}
 DEMOD_GBS_DEFAULT = 5000.0
-PER_CAPTURE_NS = 8.0           # k_clock + k_frame_warp per capture (c2: 36 us / 4096, c3: 100 us / 16384)
+PER_CAPTURE_NS = 6.0           # clock recovery + framing per capture (c2: 35 us / 4096, c3: 68 us / 16384)
 PCIE_GBS = 55.0                # pinned host -> device, one B200 on PCIe 5 x16
 
 

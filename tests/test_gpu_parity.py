@@ -130,8 +130,15 @@ def test_tx_unequal_tones_long_payloads():
     all training times, one batch mixed with an equal-tone capture."""
     rng = np.random.default_rng(48)
     cases = [(4800, 5000, 0.5), (960, 700, 0.1), (8000, 3000, 0.0), (24000, 2000, 0.02), (1600, 1, 0.5),
-             (4800, 0, 0.5), (1200, 300, 0.1), (4800, 257, 0.013)]
+             (4800, 0, 0.5), (1200, 300, 0.1), (4800, 257, 0.013),
+             # more codewords in one 65,536-frame chunk than k_synth_var stages in shared memory (4096): global searches
+             (24000, 9000, 0.02), (8000, 12000, 0.1),
+             # all-ones / all-zeros nibbles: the shortest and the longest codewords (no frames at all at 24000 baud)
+             (24000, 5000, 0.02), (8000, 6000, 0.0), (4800, 9000, 0.1), (960, 2500, 0.5)]
     pls = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for _, n, _ in cases]
+    pls[10] = b"\xff" * 5000
+    pls[11] = b"\xff" * 3000 + b"\x00" * 3000
+    pls[12] = b"\x00" * 4500 + b"\xff" * 4500
     s = A.TxSession(pls, [b for b, _, _ in cases], [O.ts_cycles(b, t) for b, _, t in cases])
     s.upload(); s.run()
     out = s.download()

@@ -229,13 +229,22 @@ __device__ __forceinline__ void var_locate(long long n, const TxDesc &d, const u
     u = (int)rem;
 }
 
-// Unequal tones: a lane synthesizes 64 consecutive frames (8 output vectors) — one var_locate, then a walk along
-// the bit sequence (both tone lengths are even, so a duplicated pair never straddles two bits) — into a
-// per-warp staging block in shared memory (XOR-swizzled: conflict-free both ways); the warp then writes its
-// 256 vectors as coalesced 128-bit stores.  (One binary search per output vector, 11 dependent global loads
-// each, made the first version run at 0.46 TB/s.)
+// Unequal tones: a lane synthesizes 64 consecutive frames (8 output vectors) into a per-warp staging block in shared
+// memory (XOR-swizzled: conflict-free both ways); the warp then writes its 256 vectors as coalesced 128-bit stores.
+//
+// Tones of at least 8 frames (4800 baud and below): one var_locate, then the lane lists the nine bits its 64 frames can
+// touch — symbol and first frame relative to the lane's — in its column of a shared-memory table (inside the coded
+// bits the symbols are cut out of one 21-bit stream built from the two payload bytes that hold the three codewords
+// involved) and emits its 32 frame pairs WITHOUT A BRANCH: per pair one table load, "has the next bit started" as a
+// select, the tone phase as a bit of the tone's mask.  ncu on the walk it replaces (a while loop per pair that
+// advanced bit by bit): 14 of 32 lanes active per instruction, 1.04 G warp instructions for 637 M frames, a third of the
+// stall samples waiting for instruction fetch — it ran at 0.85 TB/s whatever was done to its searches and its arithmetic.
+//
+// Shorter tones (8000 baud: 4 / 6 frames; 24000 baud: the mark tone has no frames at all, :81-85) keep that walk: a bit
+// list per 64 frames would not be bounded.
 constexpr int kVarVecPerLane = 8;
 constexpr int kVarBlockVecs = 32 * kVarVecPerLane;           // 256 vectors = 2048 frames per warp step
+constexpr int kVarBits = 10;                                 // nine bits per lane step and a sentinel
 
 __global__ void __launch_bounds__(kSynthThreads) k_synth_var(const uint8_t *__restrict__ pay,
                                                              const TxDesc *__restrict__ descs,
@@ -244,19 +253,91 @@ __global__ void __launch_bounds__(kSynthThreads) k_synth_var(const uint8_t *__re
                                                              int16_t *__restrict__ out)
 {
     __shared__ uint4 stage[kSynthThreads / 32][kVarBlockVecs];
+    __shared__ int32_t bits[kVarBits][kSynthThreads];        // [bit][thread]: (first frame relative to the lane's) * 4 + symbol
     const long long chunk = blockIdx.x;
     const TxDesc d = descs[chunk_cap[chunk]];
     if (d.ml == d.bf) return;                                // equal tones: k_synth
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t *ns = nib_start + d.nib_off;
     const long long nvec_cap = (d.out_len + 7) >> 3;
     const long long v0 = (chunk - d.chunk_first) * kChunkVecs;
     const long long vend = min(v0 + (long long)kChunkVecs, nvec_cap);
     uint4 *dst = reinterpret_cast<uint4 *>(out + d.out_off);
     uint4 *st = stage[warp];
+    const bool long_tones = d.ml >= 8;                       // uniform over the CTA
+    // tones of up to 64 frames as bit masks over their even phases (bit k: frame 2k is HI; tone_pair's rule, Waveforms :68-85):
+    // space = h HI, h LO (h = bf / 2); mark = q HI, q LO, q HI, q LO (q = int(bf / 4))
+    const bool use_masks = d.bf <= 64;
+    uint32_t mask_mark = 0u, mask_space = 0u;
+    if (use_masks) {
+        const int q = d.bf >> 2, h = d.bf >> 1;
+        auto below = [](int n) -> uint32_t { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); };   // bits k with k < n
+        mask_space = below((h + 1) >> 1);                                                // 2k < h
+        mask_mark = below((q + 1) >> 1) | (below((3 * q + 1) >> 1) & ~below(q));          // 2k < q  or  2q <= 2k < 3q
+    }
+    const long long first_coded = d.ts_bits + 4;
     for (long long vb = v0 + (long long)warp * kVarBlockVecs; vb < vend; vb += (long long)(kSynthThreads / 32) * kVarBlockVecs) {
         const long long vl = vb + (long long)lane * kVarVecPerLane;      // this lane's first vector
-        if (vl < vend) {
+        if (vl < vend && long_tones) {
+            long long b;
+            int u;
+            var_locate(8 * vl, d, pay, ns, b, u);
+            // ---- the nine bits from b: symbols
+            uint32_t symbits = 0u;                           // two bits per symbol (2 = the zero frames behind the last bit)
+            if (b >= first_coded && b + 8 < d.total_bits) {
+                const long long j = b - first_coded;         // coded bit index: codeword g0, place r0
+                const long long g0 = j < 0x7FFFFFFFLL ? (long long)((uint32_t)j / 7u) : j / 7;   // 32-bit divide for all but > 150 MB payloads
+                const int r0 = (int)(j - 7 * g0);
+                const long long i0 = g0 >> 1;
+                const uint32_t B0 = pay[d.pay_off + i0];
+                const uint32_t B1 = (i0 + 1 < d.pay_len) ? pay[d.pay_off + i0 + 1] : 0u;
+                const uint32_t B01 = (B0 << 8) | B1;
+                uint32_t stream = 0u;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int idx = (int)(g0 & 1) + k;       // nibble 0..3 of the two bytes, high nibble first :446-450
+                    stream |= hamming74_encode((B01 >> (12 - 4 * idx)) & 15u) << (7 * k);
+                }
+                stream >>= r0;
+#pragma unroll
+                for (int i = 0; i < 9; i++) symbits |= ((stream >> i) & 1u) << (2 * i);
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < 9; i++) symbits |= (b + i < d.total_bits ? tx_bit(b + i, d, pay) : 2u) << (2 * i);
+            }
+            // ---- first frames relative to the lane's first frame; bit 0 started u frames before it
+            int rel = -u;
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const uint32_t sy = (symbits >> (2 * i)) & 3u;
+                bits[i][tid] = rel * 4 + (int)sy;
+                rel += sy == 2u ? (1 << 20) : (sy ? d.ml : d.bf);
+            }
+            bits[9][tid] = (1 << 23) + 2;                    // never starts
+            // ---- 32 frame pairs: at most one bit starts between two of them (tones of 8 frames and more)
+            int cur = 0;
+            int curk = bits[0][tid];
+#pragma unroll
+            for (int k = 0; k < kVarVecPerLane; k++) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int o = 8 * k + 2 * j;
+                    const int nextk = bits[cur + 1][tid];
+                    const bool adv = o >= (nextk >> 2);
+                    cur += adv ? 1 : 0;
+                    curk = adv ? nextk : curk;
+                    const uint32_t sy = (uint32_t)curk & 3u;
+                    const int ph = o - (curk >> 2);
+                    if (use_masks)
+                        w[j] = sy == 2u ? 0u : ((((sy ? mask_mark : mask_space) >> ((ph >> 1) & 31)) & 1u) ? 0x7FFF7FFFu : 0x80008000u);
+                    else
+                        w[j] = tone_pair(sy, ph, d.bf);
+                }
+                const int v = lane * kVarVecPerLane + k;
+                st[v ^ ((v >> 3) & 7)] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else if (vl < vend) {
             long long b;
             int u;
             var_locate(8 * vl, d, pay, ns, b, u);
